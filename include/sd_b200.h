@@ -1,0 +1,168 @@
+/* sd_b200.h — C ABI of libsd_b200.so: the B200 (sm_100a) implementation of the
+ * speaker-diarization hot path of hzane/speech-diarization
+ * (log-mel fbank -> ECAPA-TDNN -> cosine affinity -> AHC).
+ *
+ * The reference reaches this path through Python callables only
+ * (SURVEY.md §8b); there is no native FFI in the reference.  Each entry point
+ * below therefore cites the reference callable whose arithmetic it replaces,
+ * and the modules of speech_diarization_b200 re-export those callables on top of this
+ * ABI through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - every function returns an int status, SD_OK (0) on success; it never
+ *    throws and never falls back to a CPU path.  sd_last_error() returns a
+ *    thread-local detail string for the last failure.
+ *  - pointers named *_dev are device pointers on the current CUDA device;
+ *    `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - calls are asynchronous with respect to the host unless stated otherwise.
+ *  - all matrices are row-major, f32 unless stated otherwise.
+ */
+#ifndef SD_B200_H_
+#define SD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_OK 0
+#define SD_ERR_ARG 1         /* bad argument (shape, alignment, NULL) */
+#define SD_ERR_CUDA 2        /* a CUDA runtime call or kernel launch failed */
+#define SD_ERR_DRIVER 3      /* cuTensorMapEncodeTiled unavailable / failed */
+#define SD_ERR_NOMEM 4       /* device allocation failed */
+#define SD_ERR_UNSUPPORTED 5 /* valid request outside what this build implements */
+#define SD_ERR_MISSING 6     /* a required weight tensor is missing or mis-sized */
+
+#define SD_EMB_DIM 192  /* ecapa_annote.py:11 (self.dimension = 192) */
+#define SD_N_MELS 80
+
+/* Library version (major*10000 + minor*100 + patch). */
+int sd_version(void);
+const char* sd_status_string(int status);
+const char* sd_last_error(void);
+
+/* ------------------------------------------------------------------ fbank ---
+ * Number of frames a centre-padded STFT (n_fft = win = 400, hop = 160) yields:
+ * T = 1 + n_samples / 160.  (torch.stft via torchaudio MelSpectrogram,
+ * speech_encode.py:17-30.) */
+int sd_fbank_num_frames(int n_samples);
+
+/* Log-mel filterbank features of B windows.
+ * Replaces fbank_batch (speech_encode.py:10-38) when variant == SD_FBANK_TORCHAUDIO:
+ *   reflect centre pad 200, periodic Hann(400), |rFFT|^2, 80 HTK triangles on
+ *   [20, 7900] Hz, log(x + 1e-6), and, if mean_norm, minus the per-(window, mel)
+ *   time mean (speech_encode.py:35-36).
+ * variant == SD_FBANK_SPEECHBRAIN is the front end inside
+ *   EncoderClassifier.encode_batch (call sites speech_encode.py:77,
+ *   ecapa_annote.py:22, diar_diag.py:169): zero centre pad, periodic Hamming(400),
+ *   |rFFT|^2, speechbrain triangular filters on [0, 8000] Hz, 10 log10(max(x, 1e-10)),
+ *   floor at (window max - 80 dB), then sentence mean normalisation (mean_norm).
+ * Window b starts at wav_dev + b * wav_stride (elements), so overlapping windows of
+ * one audio buffer are addressed in place (wav_stride = hop) instead of being
+ * materialised as vad.py:9-16 / frame_audio does.
+ * out_dev: [B, T, 80] f32.  Requires n_samples >= 400 (201 for the reflect pad). */
+#define SD_FBANK_TORCHAUDIO 0
+#define SD_FBANK_SPEECHBRAIN 1
+int sd_fbank_f32(const float* wav_dev, long wav_stride, int B, int n_samples, int variant,
+                 int mean_norm, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------- ECAPA-TDNN ---
+ * A plan owns the f16-repacked weights (speechbrain ECAPA_TDNN, C = 1024,
+ * attention 128, embedding 192), folded BatchNorm constants, activation
+ * workspace for up to max_batch windows of max_samples samples, and cached TMA
+ * descriptors.  Replaces the model behind using_ecapa_encoder
+ * (speech_encode.py:64-70).
+ *
+ * Weights are passed as a speechbrain-keyed state dict: names[i] is the key
+ * (e.g. "blocks.0.conv.conv.weight", "blocks.1.res2net_block.blocks.0.norm.norm.running_var",
+ * "mfa.conv.conv.weight", "asp.tdnn.conv.conv.weight", "asp.conv.conv.weight",
+ * "asp_bn.norm.weight", "fc.conv.weight"), tensors[i] a HOST pointer to the f32
+ * data in PyTorch layout, numels[i] its element count.  Synchronous. */
+typedef struct SdEcapaPlan SdEcapaPlan;
+int sd_ecapa_plan_create(const char* const* names, const float* const* tensors,
+                         const int64_t* numels, int n_tensors, int max_batch, int max_samples,
+                         SdEcapaPlan** plan_out);
+int sd_ecapa_plan_destroy(SdEcapaPlan* plan);
+
+/* Embeddings of B windows: speechbrain fbank + sentence-mean norm + ECAPA-TDNN.
+ * Replaces EncoderClassifier.encode_batch(wavs).squeeze(1) as called by
+ * ecapa_encode_batch (speech_encode.py:73-78) and ECAPAEncoder.forward
+ * (ecapa_annote.py:13-22); like them it uses no wav_lens (zero padding is
+ * signal) and does not L2-normalise unless l2_normalize != 0
+ * (then e / (||e|| + 1e-8), the consumers' convention,
+ * anti_stick_diarize.py:176,430).
+ * emb_dev: [B, 192] f32.  B <= max_batch, 400 <= n_samples <= max_samples. */
+int sd_ecapa_embed(SdEcapaPlan* plan, const float* wav_dev, long wav_stride, int B, int n_samples,
+                   int l2_normalize, float* emb_dev, void* stream);
+
+/* Same trunk from precomputed features feats_dev [B, T, 80] f32 (already
+ * normalised); used by the parity tests to isolate the trunk. */
+int sd_ecapa_forward_feats(SdEcapaPlan* plan, const float* feats_dev, int B, int T,
+                           int l2_normalize, float* emb_dev, void* stream);
+
+/* Test hook: copy an internal activation of the LAST forward to out_dev as f32
+ * [B, T, C] (interior frames, channels-last).  name in {"feats","block0","b1.tdnn1",
+ * "b1.res2net","b1.tdnn2","b1.out","b2.out","b3.out","mfa","asp.attn"} or
+ * [B, C] for {"b1.se","asp.mean","asp.std","pooled"}.  *C_out receives C. */
+int sd_ecapa_debug_fetch(SdEcapaPlan* plan, const char* name, float* out_dev, int* C_out,
+                         void* stream);
+
+/* FLOPs (2 * MACs of the dense contractions actually issued, padding excluded)
+ * of one window of T frames — the figure bench.py's roofline uses. */
+double sd_ecapa_flops_per_window(int T);
+
+/* ------------------------------------------------- affinity and clustering ---
+ * out[i, :] = x[i, :] / (||x[i, :]|| + eps)   (anti_stick_diarize.py:176,203,430) */
+int sd_l2norm_f32(const float* x_dev, int N, int D, float eps, float* out_dev, void* stream);
+
+/* Cosine DISTANCE row block:  out[i - row0, j] = 1 - cos(x_i, x_j), row0 <= i < row0 + rows,
+ * 0 <= j < N — the `D = 1 - cosine_similarity(embs)` of cluster_embeddings
+ * (diar_diag.py:215,219) and cluster_hdbscan (anti_stick_diarize.py:177), with
+ * sklearn's internal row normalisation (zero rows stay zero).  Tensor-core GEMM
+ * on a split-f16 (hi + lo*2^-11) representation; |error| <= 1e-5 absolute.
+ * emb_dev [N, D] f32, D % 64 == 0, D <= 512.  out_dev [rows, N] f32 (ld = N).
+ * out_f64_dev, if not NULL, receives the same values widened to f64 (the AHC
+ * working matrix).  workspace_dev: sd_affinity_workspace_bytes(N, D) bytes. */
+size_t sd_affinity_workspace_bytes(int N, int D);
+int sd_cosine_distance_rowblock(const float* emb_dev, int N, int D, int row0, int rows,
+                                float* out_dev, double* out_f64_dev, void* workspace_dev,
+                                void* stream);
+
+/* Average-linkage agglomerative clustering of a precomputed distance matrix with
+ * a distance threshold: AgglomerativeClustering(n_clusters=None,
+ * linkage="average", metric="precomputed", distance_threshold=threshold)
+ * .fit_predict(D) (diar_diag.py:221-226).  Merges every pair whose linkage
+ * distance is < threshold; Lance-Williams updates in f64 on the f32-rounded
+ * input, as scipy does.  Labels are numbered by each cluster's smallest member
+ * (0, 1, ... in order of first appearance) — equal to sklearn's up to a
+ * permutation.
+ * dist_dev: [N, N] f32 symmetric (only read).  labels_dev: [N] int32.
+ * n_clusters_dev: [1] int32.  workspace_dev: sd_ahc_workspace_bytes(N) bytes. */
+size_t sd_ahc_workspace_bytes(int N);
+int sd_ahc_average_f32(const float* dist_dev, int N, float threshold, int32_t* labels_dev,
+                       int32_t* n_clusters_dev, void* workspace_dev, void* stream);
+
+/* best[i] = argmax_k <x_i, c_k>, score[i] = that maximum (frame_reassign,
+ * anti_stick_diarize.py:433-434).  x_dev [N, D], cent_dev [K, D], K <= 64.
+ * First maximum wins, as numpy.argmax. score_dev may be NULL. */
+int sd_window_argmax(const float* x_dev, const float* cent_dev, int N, int K, int D,
+                     int32_t* best_dev, float* score_dev, void* stream);
+
+/* sims[i] = <x_i, x_{i+1}> / (||x_i|| ||x_{i+1}|| + 1e-8), 0 <= i < N - 1
+ * (scd_split_segments, anti_stick_diarize.py:102-104). */
+int sd_adjacent_cosine(const float* x_dev, int N, int D, float* sims_dev, void* stream);
+
+/* ------------------------------------------------------------ debug / test ---
+ * Raw tensor-core GEMM used by the unit tests of the tcgen05 kernel:
+ *   D[m, n] = sum_{j < taps} sum_{k < K} A[m + (j - taps/2) * dil, k] * B[n, j*K + k]
+ * A [M, K] f16 (rows outside [0, M) read as zero), B [N, taps*K] f16, D [M, N] f32.
+ * K % 64 == 0, n_tile % 16 == 0 and <= 256. */
+int sd_debug_gemm_f16(const void* A_dev, int M, int K, const void* B_dev, int N, int taps, int dil,
+                      int n_tile, float* D_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SD_B200_H_ */

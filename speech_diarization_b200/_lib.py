@@ -1,0 +1,78 @@
+"""ctypes loader for libsd_b200.so (the C-ABI declared in include/sd_b200.h).
+
+There is deliberately no fallback: if the CUDA extension is missing or a call
+fails, the caller gets an exception (BASELINE.json north_star: "no CPU fallback").
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_long, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsd_b200.so")
+
+
+class SdError(RuntimeError):
+    """A libsd_b200 entry point returned a non-zero status."""
+
+
+# name -> (restype, argtypes); must list every symbol include/sd_b200.h declares
+# (tests/test_abi.py checks the two against each other).
+SIGNATURES = {
+    "sd_version": (c_int, []),
+    "sd_status_string": (c_char_p, [c_int]),
+    "sd_last_error": (c_char_p, []),
+    "sd_fbank_num_frames": (c_int, [c_int]),
+    "sd_fbank_f32": (c_int, [c_void_p, c_long, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sd_ecapa_plan_create": (c_int, [POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_int, c_int, POINTER(c_void_p)]),
+    "sd_ecapa_plan_destroy": (c_int, [c_void_p]),
+    "sd_ecapa_embed": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sd_ecapa_forward_feats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sd_ecapa_debug_fetch": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int), c_void_p]),
+    "sd_ecapa_flops_per_window": (c_double, [c_int]),
+    "sd_l2norm_f32": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "sd_affinity_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "sd_cosine_distance_rowblock": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sd_ahc_workspace_bytes": (c_size_t, [c_int]),
+    "sd_ahc_average_f32": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sd_window_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "sd_adjacent_cosine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sd_debug_gemm_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library and bind every declared symbol. Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SdError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(speech_diarization_b200/csrc/build.sh). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.sd_status_string(status).decode()
+        detail = lib.sd_last_error().decode()
+        raise SdError(f"{what or 'libsd_b200'}: status {status} ({msg}) {detail}")
+
+
+def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream, so our launches are ordered with torch's."""
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,95 @@
+// gemm_host.cuh — host side of gemm_tc.cuh: TMA tensor-map encoding (driver entry
+// point fetched at run time, so the library loads on a box without libcuda) and
+// the launch helper.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include "gemm_tc.cuh"
+#include "sd_status.h"
+
+namespace sd {
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled get_tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  return fn;
+}
+
+// 2-D f16 tensor [rows][cols] with row pitch `ld` elements; box = 64 columns x box_rows,
+// 128-byte swizzle, out-of-bounds elements read as zero (negative coordinates allowed).
+inline int make_tmap_f16(CUtensorMap* m, const void* base, long rows, long cols, long ld,
+                         int box_rows) {
+  PFN_tmapEncodeTiled enc = get_tmap_encoder();
+  if (!enc) return SD_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 || box_rows < 1 || box_rows > 256)
+    return SD_ERR_ARG;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SD_OK : SD_ERR_DRIVER;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int EPI, int MAX_BN>
+inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
+  using Cfg = GemmCfg<MAX_BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<EPI, MAX_BN>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::SMEM_BYTES) != cudaSuccess)
+      return SD_ERR_CUDA;
+    attr_set = true;
+  }
+  const int tiles = P.num_m_blocks * P.num_n_blocks;
+  if (tiles <= 0) return SD_OK;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<EPI, MAX_BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(P);
+  return cudaGetLastError() == cudaSuccess ? SD_OK : SD_ERR_CUDA;
+}
+
+// Chooses the shared-memory configuration from n_tile.
+template <int EPI>
+inline int launch_gemm(const GemmParams& P, cudaStream_t stream) {
+  if (P.n_tile % 16 || P.n_tile < 16 || P.n_tile > 256 || P.num_kiters < 1 ||
+      P.num_kiters > MAX_KITERS || P.acc_slots * P.n_tile > TMEM_COLS)
+    return SD_ERR_ARG;
+  if (P.n_tile <= 128) return launch_gemm_t<EPI, 128>(P, stream);
+  return launch_gemm_t<EPI, 256>(P, stream);
+}
+
+inline void init_params(GemmParams& P) {
+  std::memset(&P, 0, sizeof(P));
+  P.acc_slots = 1;
+  P.epi.Tp = 1;
+}
+
+}  // namespace sd

@@ -1,0 +1,488 @@
+// gemm_tc.cuh — one persistent, warp-specialised tcgen05 GEMM kernel that carries
+// every tensor-core contraction of the hot path:
+//
+//   D[128 x n_tile] (f32, TMEM)  =  sum over "k-iterations"  A_tile[128 x 64] * B_tile[n_tile x 64]^T
+//
+// A k-iteration is one 64-element K chunk; a small table (KIter) says, for each
+// one, which column of the A / B tensors to fetch, which ROW OFFSET to apply to
+// A (that is how the dilated k=3 / k=5 convolutions of ECAPA-TDNN become
+// implicit GEMMs over a channels-last activation tensor — the taps are row
+// shifts), and which accumulator slot it feeds (the affinity kernel keeps three
+// partial products apart).  Operands are f16, K-major, fetched by TMA with the
+// 128-byte swizzle; accumulators are f32 in TMEM, double-buffered so that the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..5 = epilogue (each owns the TMEM lane quarter warp_idx % 4).
+//
+// Epilogues (template parameter EPI):
+//   EPI_F32   raw f32 store (unit tests)
+//   EPI_TDNN  speechbrain TDNNBlock tail: +bias -> ReLU -> BatchNorm(eval) [-> tanh], f16
+//             channels-last store, with the reflect halo the next dilated conv needs
+//             materialised, the Res2Net "x_{i+1} + y_i" sum emitted on the side, and
+//             the ASP per-utterance context bias            (reference: speechbrain
+//             ECAPA_TDNN, call sites speech_encode.py:77, ecapa_annote.py:22)
+//   EPI_POOL  attentive-statistics pooling: rows = channels, columns = the frames of ONE
+//             utterance, so softmax over time and the weighted mean/std are thread-local
+//             (SURVEY App. A.2 AttentiveStatisticsPooling)
+//   EPI_AFF   cosine distance 1 - S from split-f16 partial products
+//             (diar_diag.py:215,219; anti_stick_diarize.py:176-177)
+#pragma once
+#include <cuda.h>
+#include "sd_ptx.cuh"
+
+namespace sd {
+
+constexpr int BM = 128;        // UMMA M: rows of the A tile = TMEM lanes
+constexpr int BK = 64;         // f16 elements per K chunk = one 128-byte swizzle span
+constexpr int UMMA_K = 16;     // K per tcgen05.mma for 16-bit operands
+constexpr int MAX_KITERS = 48; // 3072 / 64 (the MFA layer)
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+enum { EPI_F32 = 0, EPI_TDNN = 1, EPI_POOL = 2, EPI_AFF = 3 };
+enum {
+  EF_RELU_BN = 1,   // x = relu(x + bias) * scale + shift
+  EF_REFLECT = 2,   // store interior rows only and mirror them into the halo rows
+  EF_TANH = 4,      // tanh after BN (ASP attention TDNN)
+  EF_UTT_BIAS = 8,  // bias comes from a per-utterance table instead of `bias`
+};
+
+struct KIter {
+  int a_col;      // element column in A's tensor map
+  int a_row_off;  // row shift applied to the A tile (conv tap * dilation)
+  int b_col;      // element column in B's tensor map
+  int slot;       // accumulator slot (0 unless EPI_AFF)
+  int accum;      // 0 = first k-iteration of this slot (overwrite), 1 = accumulate
+};
+
+struct EpiParams {
+  int flags;
+  int M_rows;   // valid rows (A side) — rows >= M_rows are never stored
+  int N_cols;   // valid columns (B side)
+  // utterance geometry of the channels-last activation tensors:
+  // rows [b*Tp, (b+1)*Tp), interior frame t at row b*Tp + H + t, 0 <= t < T.
+  int Tp, T, H;
+  // main output
+  void* out;
+  int ld_out;       // elements
+  int out_col_off;  // elements
+  const float* bias;   // [N] (EPI_TDNN) — ignored with EF_UTT_BIAS
+  const float* scale;  // [N]
+  const float* shift;  // [N]
+  // second copy of the first `out2_cols` columns (Res2Net chunk 0 passes through)
+  __half* out2;
+  int ld_out2;
+  int out2_cols;
+  // Res2Net chain: sum_out[r, c] = y[r, c] + add_src[r, add_col_off + c]
+  const __half* add_src;
+  int ld_add;
+  int add_col_off;
+  __half* sum_out;
+  int ld_sum;
+  // ASP context bias [num_utts, N]
+  const float* utt_bias;
+  // EPI_POOL: h activations, global mean, pooled output [B, 2*C]
+  const __half* h;
+  int ld_h;
+  const float* gmean;  // [B, C]
+  float* pooled;       // [B, 2*C]: mean then std
+  int C;
+  // EPI_AFF
+  double* out_f64;  // optional second copy as f64 (AHC working matrix), same ld
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap tmapA;
+  CUtensorMap tmapB;
+  int num_m_blocks, num_n_blocks, num_kiters;
+  int n_tile;      // UMMA N and rows of the B box
+  int a_row_base;  // added to every A row coordinate (row-block sharding)
+  int acc_slots;   // 1, or 3 for EPI_AFF
+  uint32_t idesc;
+  KIter kit[MAX_KITERS];
+  EpiParams epi;
+};
+
+template <int MAX_BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;         // 16 KB
+  static constexpr int B_BYTES = MAX_BN * BK * 2;     // 16 / 32 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (MAX_BN == 256) ? 4 : 6;
+  static constexpr int EPI_SMEM_FLOATS = 3 * 256;     // bias/scale/shift of one n block
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_FLOATS * 4 + 256 + 1024;
+};
+
+// ------------------------------------------------------------------ epilogues
+__device__ __forceinline__ void epi_named_barrier() {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// raw f32
+__device__ __forceinline__ void epilogue_f32(const GemmParams& P, int m_blk, int n_blk,
+                                             uint32_t tmem_acc, int quarter, int lane) {
+  const EpiParams& E = P.epi;
+  const int r = m_blk * BM + quarter * 32 + lane;
+  float* out = reinterpret_cast<float*>(E.out);
+  for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+    uint32_t v[16];
+    __syncwarp();
+    tmem_ld16(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    if (r < E.M_rows) {
+      const int col0 = n_blk * P.n_tile + c0;
+      float* dst = out + static_cast<size_t>(r) * E.ld_out + E.out_col_off + col0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < E.N_cols) dst[j] = __uint_as_float(v[j]);
+    }
+  }
+}
+
+// TDNN tail. `sp` = this n block's {bias, scale, shift} staged in shared memory.
+__device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, int n_blk,
+                                              uint32_t tmem_acc, int quarter, int lane,
+                                              const float* sp) {
+  const EpiParams& E = P.epi;
+  const int r = m_blk * BM + quarter * 32 + lane;
+  const int b = r / E.Tp;
+  const int t = r - b * E.Tp - E.H;
+  bool valid = r < E.M_rows;
+  int r2 = -1, r3 = -1;  // mirrored halo rows
+  if (E.flags & EF_REFLECT) {
+    valid = valid && t >= 0 && t < E.T;
+    if (valid) {
+      if (t >= 1 && t <= E.H) r2 = b * E.Tp + E.H - t;
+      if (t >= E.T - 1 - E.H && t <= E.T - 2) r3 = b * E.Tp + E.H + 2 * (E.T - 1) - t;
+    }
+  }
+  __half* out = reinterpret_cast<__half*>(E.out);
+  const float* ub = (E.flags & EF_UTT_BIAS) ? E.utt_bias + static_cast<size_t>(b) * E.N_cols : nullptr;
+  for (int c0 = 0; c0 < P.n_tile; c0 += 32) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld32(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    if (!valid) continue;
+    const int col0 = n_blk * P.n_tile + c0;  // column within this layer's output
+    float x[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float a = __uint_as_float(v[j]);
+      if (E.flags & EF_UTT_BIAS) a += __ldg(ub + col0 + j);
+      else a += sp[c0 + j];
+      if (E.flags & EF_RELU_BN) a = fmaxf(a, 0.f) * sp[256 + c0 + j] + sp[512 + c0 + j];
+      if (E.flags & EF_TANH) a = tanhf(a);
+      x[j] = a;
+    }
+    uint4 pk[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      pk[q].x = pack_half2(x[8 * q + 0], x[8 * q + 1]);
+      pk[q].y = pack_half2(x[8 * q + 2], x[8 * q + 3]);
+      pk[q].z = pack_half2(x[8 * q + 4], x[8 * q + 5]);
+      pk[q].w = pack_half2(x[8 * q + 6], x[8 * q + 7]);
+    }
+    const size_t coff = static_cast<size_t>(E.out_col_off + col0);
+    {
+      uint4* d = reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * E.ld_out + coff);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d[q] = pk[q];
+    }
+    if (r2 >= 0) {
+      uint4* d = reinterpret_cast<uint4*>(out + static_cast<size_t>(r2) * E.ld_out + coff);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d[q] = pk[q];
+    }
+    if (r3 >= 0) {
+      uint4* d = reinterpret_cast<uint4*>(out + static_cast<size_t>(r3) * E.ld_out + coff);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d[q] = pk[q];
+    }
+    if (E.out2 != nullptr && col0 < E.out2_cols) {
+      uint4* d = reinterpret_cast<uint4*>(E.out2 + static_cast<size_t>(r) * E.ld_out2 + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d[q] = pk[q];
+    }
+    if (E.sum_out != nullptr) {
+      // next Res2Net input: x_{i+1} + y_i, built from the f16-rounded y_i the next conv
+      // would otherwise have read back (keeps the sum bit-identical to an unfused chain).
+      const uint4* a4 = reinterpret_cast<const uint4*>(
+          E.add_src + static_cast<size_t>(r) * E.ld_add + E.add_col_off + col0);
+      uint4 sk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 av = __ldg(a4 + q);
+        const __half2* ah = reinterpret_cast<const __half2*>(&av);
+        const __half2* yh = reinterpret_cast<const __half2*>(&pk[q]);
+        __half2 s[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 fa = __half22float2(ah[e]);
+          float2 fy = __half22float2(yh[e]);
+          s[e] = __floats2half2_rn(fa.x + fy.x, fa.y + fy.y);
+        }
+        sk[q] = *reinterpret_cast<uint4*>(s);
+      }
+      uint4* d = reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r) * E.ld_sum + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d[q] = sk[q];
+      if (r2 >= 0) {
+        uint4* d2 = reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r2) * E.ld_sum + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d2[q] = sk[q];
+      }
+      if (r3 >= 0) {
+        uint4* d3 = reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r3) * E.ld_sum + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d3[q] = sk[q];
+      }
+    }
+  }
+}
+
+// Attentive statistics pooling. Tile rows = 128 channels, tile columns = the Tp
+// rows of utterance n_blk, so each thread owns one channel's logits over time.
+// The conv bias of the attention's output layer is constant over time and
+// cancels in the softmax, so it is never added.
+__device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, int n_blk,
+                                              uint32_t tmem_acc, int quarter, int lane) {
+  const EpiParams& E = P.epi;
+  const int ch = m_blk * BM + quarter * 32 + lane;
+  const int b = n_blk;
+  const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+  const bool chv = ch < E.C;
+  // pass 1: max over interior frames
+  float mx = -INFINITY;
+  for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tbase + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int t = c0 + j - E.H;
+      if (t >= 0 && t < E.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+  }
+  // pass 2: softmax-weighted first/second moments about the global mean g
+  const float g = chv ? E.gmean[static_cast<size_t>(b) * E.C + ch] : 0.f;
+  const __half* hcol = E.h + static_cast<size_t>(b) * E.Tp * E.ld_h + (chv ? ch : 0);
+  float se = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tbase + c0, v);
+    float xv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int t = c0 + j - E.H;
+      xv[j] = (t >= 0 && t < E.T) ? __half2float(hcol[static_cast<size_t>(c0 + j) * E.ld_h]) : 0.f;
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int t = c0 + j - E.H;
+      if (t >= 0 && t < E.T) {
+        const float e = __expf(__uint_as_float(v[j]) - mx);
+        const float x = xv[j] - g;
+        se += e;
+        s1 = fmaf(e, x, s1);
+        s2 = fmaf(e * x, x, s2);
+      }
+    }
+  }
+  if (chv) {
+    const float inv = 1.f / se;
+    const float m1 = s1 * inv;
+    const float var = fmaxf(s2 * inv - m1 * m1, 1e-12f);
+    E.pooled[static_cast<size_t>(b) * 2 * E.C + ch] = g + m1;
+    E.pooled[static_cast<size_t>(b) * 2 * E.C + E.C + ch] = sqrtf(var);
+  }
+}
+
+// Cosine distance from the three split-f16 partial products:
+//   slot0 = hi.hi   slot1 = hi.lo'   slot2 = lo'.hi      (lo' = lo * 2^11)
+//   S = slot0 + (slot1 + slot2) * 2^-11 ,  D = 1 - S      (f32, as sklearn computes it)
+// slot1 + slot2 is commutative, so D is exactly symmetric.
+__device__ __forceinline__ void epilogue_aff(const GemmParams& P, int m_blk, int n_blk,
+                                             uint32_t tmem_acc, int quarter, int lane) {
+  const EpiParams& E = P.epi;
+  const int r = m_blk * BM + quarter * 32 + lane;
+  const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+  float* out = reinterpret_cast<float*>(E.out);
+  for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+    uint32_t v0[16], v1[16], v2[16];
+    __syncwarp();
+    tmem_ld16(tbase + c0, v0);
+    tmem_ld16(tbase + P.n_tile + c0, v1);
+    tmem_ld16(tbase + 2 * P.n_tile + c0, v2);
+    tmem_ld_wait();
+    const int col0 = n_blk * P.n_tile + c0;
+    if (r >= E.M_rows || col0 >= E.N_cols) continue;
+    float d[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float s = __uint_as_float(v0[j]) +
+                      (__uint_as_float(v1[j]) + __uint_as_float(v2[j])) * 4.8828125e-4f;
+      d[j] = 1.0f - s;
+    }
+    const size_t off = static_cast<size_t>(r) * E.ld_out + col0;
+    if (col0 + 16 <= E.N_cols && (E.ld_out & 3) == 0) {
+      float4* d4 = reinterpret_cast<float4*>(out + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d4[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < E.N_cols) out[off + j] = d[j];
+    }
+    if (E.out_f64 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < E.N_cols) E.out_f64[off + j] = static_cast<double>(d[j]);
+    }
+  }
+}
+
+// --------------------------------------------------------------------- kernel
+template <int EPI, int MAX_BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ GemmParams P) {
+  using Cfg = GemmCfg<MAX_BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128-byte swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  float* epi_sp = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_sp + Cfg::EPI_SMEM_FLOATS);
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + Cfg::STAGES;      // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = P.num_m_blocks * P.num_n_blocks;
+  const int acc_stages = (P.acc_slots * P.n_tile <= 256) ? 2 : 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&P.tmapA);
+      tma_prefetch_desc(&P.tmapB);
+      for (int s = 0; s < Cfg::STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tfull_bar[s], 1);
+        mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t tx = Cfg::A_BYTES + static_cast<uint32_t>(P.n_tile) * BK * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / P.num_n_blocks;
+        const int n_blk = tile - m_blk * P.num_n_blocks;
+        for (int k = 0; k < P.num_kiters; ++k) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &P.tmapA, &full_bar[stage], P.kit[k].a_col,
+                      P.a_row_base + m_blk * BM + P.kit[k].a_row_off);
+          tma_load_2d(sa + Cfg::A_BYTES, &P.tmapB, &full_bar[stage], P.kit[k].b_col,
+                      n_blk * P.n_tile);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * 256;
+        for (int k = 0; k < P.num_kiters; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint64_t da = make_smem_desc_sw128(a_addr);
+          const uint64_t db = make_smem_desc_sw128(b_addr);
+          const uint32_t d_addr = acc + P.kit[k].slot * P.n_tile;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            // advance 16 elements = 32 bytes inside the swizzle span: +2 in the (addr>>4) field
+            umma_f16(d_addr, da + 2 * kk, db + 2 * kk, P.idesc,
+                     (P.kit[k].accum | kk) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (++as == acc_stages) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / P.num_n_blocks;
+      const int n_blk = tile - m_blk * P.num_n_blocks;
+      if (EPI == EPI_TDNN) {
+        // stage this n block's per-column constants
+        epi_named_barrier();  // previous tile's readers are done
+        for (int i = et; i < P.n_tile; i += 128) {
+          const int c = n_blk * P.n_tile + i;
+          const bool ok = c < P.epi.N_cols;
+          epi_sp[i] = (ok && P.epi.bias) ? P.epi.bias[c] : 0.f;
+          epi_sp[256 + i] = (ok && P.epi.scale) ? P.epi.scale[c] : 1.f;
+          epi_sp[512 + i] = (ok && P.epi.shift) ? P.epi.shift[c] : 0.f;
+        }
+        epi_named_barrier();
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + as * 256;
+      if (EPI == EPI_F32) epilogue_f32(P, m_blk, n_blk, acc, quarter, lane);
+      if (EPI == EPI_TDNN) epilogue_tdnn(P, m_blk, n_blk, acc, quarter, lane, epi_sp);
+      if (EPI == EPI_POOL) epilogue_pool(P, m_blk, n_blk, acc, quarter, lane);
+      if (EPI == EPI_AFF) epilogue_aff(P, m_blk, n_blk, acc, quarter, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == acc_stages) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace sd
