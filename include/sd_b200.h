@@ -103,9 +103,10 @@ int sd_ecapa_forward_feats(SdEcapaPlan* plan, const float* feats_dev, int B, int
                            int l2_normalize, float* emb_dev, void* stream);
 
 /* Test hook: copy an internal activation of the LAST forward to out_dev as f32
- * [B, T, C] (interior frames, channels-last).  name in {"feats","block0","b1.tdnn1",
- * "b1.res2net","b1.tdnn2","b1.out","b2.out","b3.out","mfa","asp.attn"} or
- * [B, C] for {"b1.se","asp.mean","asp.std","pooled"}.  *C_out receives C. */
+ * [B, T, C] (interior frames, channels-last) for name in {"feats" (C=80), "block0",
+ * "b1.out", "b2.out", "b3.out", "b3.tdnn1", "b3.res2net", "b3.tdnn2" (C=1024),
+ * "mfa" (C=3072), "asp.attn" (C=128)}, or [B, C] for {"b3.se" (1024), "asp.stats"
+ * (6144 = mean|std), "asp.uttbias" (128), "pooled" (6144)}.  *C_out receives C. */
 int sd_ecapa_debug_fetch(SdEcapaPlan* plan, const char* name, float* out_dev, int* C_out,
                          void* stream);
 
@@ -141,7 +142,7 @@ int sd_cosine_distance_rowblock(const float* emb_dev, int N, int D, int row0, in
  * dist_dev: [N, N] f32 symmetric (only read).  labels_dev: [N] int32.
  * n_clusters_dev: [1] int32.  workspace_dev: sd_ahc_workspace_bytes(N) bytes. */
 size_t sd_ahc_workspace_bytes(int N);
-int sd_ahc_average_f32(const float* dist_dev, int N, float threshold, int32_t* labels_dev,
+int sd_ahc_average_f32(const float* dist_dev, int N, double threshold, int32_t* labels_dev,
                        int32_t* n_clusters_dev, void* workspace_dev, void* stream);
 
 /* best[i] = argmax_k <x_i, c_k>, score[i] = that maximum (frame_reassign,

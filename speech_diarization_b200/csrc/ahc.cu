@@ -1,0 +1,311 @@
+// ahc.cu — average-linkage agglomerative clustering with a distance threshold on the GPU
+// (SURVEY.md §2.1 K11).
+//
+// Replaces  AgglomerativeClustering(n_clusters=None, linkage="average", metric="precomputed",
+//           distance_threshold=1-cos_thr).fit_predict(D)      (/root/reference/diar_diag.py:221-226),
+// which runs scipy's single-threaded nn_chain in float64 on the f32 distance matrix.
+//
+// Algorithm: average linkage (UPGMA) is REDUCIBLE, so every pair of reciprocal nearest
+// neighbours (RNN) is a merge of the final dendrogram at exactly its current distance, no
+// matter what is merged elsewhere first.  Instead of N-1 dependent merges we therefore run
+// ROUNDS; each round
+//   A  recomputes the nearest neighbour (argmin over the row) of every "dirty" cluster,
+//   B  collects all RNN pairs whose distance is < threshold,
+//   C  applies the Lance-Williams update  d(k, i+j) = (n_i d(k,i) + n_j d(k,j)) / (n_i + n_j)
+//      for all those pairs at once (rows first, then the pair x pair corners, then the
+//      mirrored columns, which keeps the matrix exactly symmetric),
+//   D  retires the absorbed clusters and marks as dirty only the merged rows and the rows
+//      whose cached nearest neighbour was merged (reducibility keeps every other cache valid).
+// It stops when no RNN pair is below the threshold, which — average linkage being monotone —
+// is the flat clustering sklearn cuts at `distance_threshold`.  The whole loop is ONE
+// persistent cooperative kernel (grid-wide barriers between phases, no host round trips).
+// Arithmetic is f64 on the f32-rounded input, as in scipy.  The matrix is HBM-resident
+// (8 N^2 bytes: 3.2 GB at N = 20k, 20 GB at 50k).
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sd_ptx.cuh"
+#include "sd_status.h"
+
+namespace cg = cooperative_groups;
+using namespace sd;
+
+namespace {
+
+constexpr int AHC_THREADS = 256;
+
+struct AhcState {
+  double* D;        // [N, N]
+  double* nn_dist;  // [N]
+  int* nn_idx;      // [N]
+  int* size;        // [N]
+  int* active;      // [N] 1 = live cluster
+  int* parent;      // [N] merge forest (root = smallest member)
+  int* role;        // [N] -1 none, else 2*pair (absorbing i) / 2*pair+1 (absorbed j) in this round
+  int* dirty_list;  // [N]
+  int* pair_i;      // [N/2]
+  int* pair_j;      // [N/2]
+  int* counters;    // [0] n_dirty(cur) [1] n_dirty(next) [2] n_pairs [3] rounds [4] merges
+  int N;
+  double thr;
+};
+
+// f32 [N,N] -> f64 [N,N], symmetrised from the upper triangle (sklearn reads D[i,j], i<j).
+__global__ void __launch_bounds__(256)
+ahc_init_matrix_kernel(const float* __restrict__ dist, int N, double* __restrict__ D) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bi > bj) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    tile[r][tx] = (i < N && j < N) ? dist[static_cast<size_t>(i) * N + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    if (i < N && j < N && (bi < bj || i <= j)) D[static_cast<size_t>(i) * N + j] = tile[r][tx];
+    // mirrored element: row j-block, column i-block
+    const int mi = bj * 32 + r, mj = bi * 32 + tx;  // D[mi, mj] = tile[tx][r]
+    if (mi < N && mj < N && (bi < bj || mj < mi)) D[static_cast<size_t>(mi) * N + mj] = tile[tx][r];
+  }
+}
+
+__global__ void ahc_init_state_kernel(AhcState S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S.N) {
+    S.size[i] = 1;
+    S.active[i] = 1;
+    S.parent[i] = i;
+    S.role[i] = -1;
+    S.dirty_list[i] = i;
+    S.nn_idx[i] = -1;
+    S.nn_dist[i] = 1e300;
+  }
+  if (i == 0) {
+    S.counters[0] = S.N;
+    S.counters[1] = 0;
+    S.counters[2] = 0;
+    S.counters[3] = 0;
+    S.counters[4] = 0;
+  }
+}
+
+__device__ __forceinline__ void argmin_combine(double& d, int& i, double od, int oi) {
+  if (od < d || (od == d && oi < i)) { d = od; i = oi; }
+}
+
+__global__ void __launch_bounds__(AHC_THREADS)
+ahc_rounds_kernel(AhcState S) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red_d[AHC_THREADS / 32];
+  __shared__ int red_i[AHC_THREADS / 32];
+  const int N = S.N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gtid = blockIdx.x * AHC_THREADS + tid;
+  const int gthreads = gridDim.x * AHC_THREADS;
+  int cur = 0;  // which dirty counter is current
+
+  for (int round = 0; round < N; ++round) {
+    // ---- A: nearest neighbour of every dirty row (one CTA per row)
+    const int n_dirty = S.counters[cur];
+    for (int q = blockIdx.x; q < n_dirty; q += gridDim.x) {
+      const int r = S.dirty_list[q];
+      const double* row = S.D + static_cast<size_t>(r) * N;
+      double bd = 1e300;
+      int bi = 0x7fffffff;
+      for (int k = tid; k < N; k += AHC_THREADS) {
+        if (k != r && S.active[k]) argmin_combine(bd, bi, row[k], k);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        argmin_combine(bd, bi, od, oi);
+      }
+      if (lane == 0) { red_d[warp] = bd; red_i[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < AHC_THREADS / 32; ++w) argmin_combine(bd, bi, red_d[w], red_i[w]);
+        S.nn_dist[r] = bd;
+        S.nn_idx[r] = bi == 0x7fffffff ? -1 : bi;
+      }
+      __syncthreads();
+    }
+    grid.sync();
+    if (gtid == 0) { S.counters[cur] = 0; S.counters[2] = 0; }
+    grid.sync();
+
+    // ---- B: reciprocal nearest neighbours below the threshold
+    for (int r = gtid; r < N; r += gthreads) {
+      if (!S.active[r]) continue;
+      const int j = S.nn_idx[r];
+      if (j > r && S.nn_dist[r] < S.thr && S.nn_idx[j] == r) {
+        const int p = atomicAdd(&S.counters[2], 1);
+        S.pair_i[p] = r;
+        S.pair_j[p] = j;
+        S.role[r] = 2 * p;
+        S.role[j] = 2 * p + 1;
+      }
+    }
+    grid.sync();
+    const int n_pairs = S.counters[2];
+    if (n_pairs == 0) break;
+
+    // ---- C1: rows.  D[i,k] <- (n_i D[i,k] + n_j D[j,k]) / (n_i + n_j) for every k
+    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+      const int i = S.pair_i[p], j = S.pair_j[p];
+      const double ni = S.size[i], nj = S.size[j], inv = ni + nj;
+      double* ri = S.D + static_cast<size_t>(i) * N;
+      const double* rj = S.D + static_cast<size_t>(j) * N;
+      for (int k = tid; k < N; k += AHC_THREADS) ri[k] = (ni * ri[k] + nj * rj[k]) / inv;
+    }
+    grid.sync();
+    // ---- C2: corners between two merged clusters (upper triangle only, i_p < i_q)
+    for (long e = gtid; e < static_cast<long>(n_pairs) * n_pairs; e += gthreads) {
+      const int p = static_cast<int>(e / n_pairs), q = static_cast<int>(e % n_pairs);
+      const int ip = S.pair_i[p], iq = S.pair_i[q], jq = S.pair_j[q];
+      if (ip < iq) {
+        const double ni = S.size[iq], nj = S.size[jq];
+        double* row = S.D + static_cast<size_t>(ip) * N;
+        row[iq] = (ni * row[iq] + nj * row[jq]) / (ni + nj);
+      }
+    }
+    grid.sync();
+    // ---- C3: mirror row i_p into column i_p (and the lower corners from the upper ones)
+    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+      const int i = S.pair_i[p];
+      double* ri = S.D + static_cast<size_t>(i) * N;
+      for (int k = tid; k < N; k += AHC_THREADS) {
+        if (k == i || !S.active[k]) continue;
+        const int rk = S.role[k];
+        if (rk >= 0 && (rk & 1)) continue;  // absorbed this round
+        if (rk >= 0 && k < i) ri[k] = S.D[static_cast<size_t>(k) * N + i];
+        else S.D[static_cast<size_t>(k) * N + i] = ri[k];
+      }
+    }
+    grid.sync();
+    // ---- D: retire absorbed clusters, mark dirty rows for the next round
+    const int nxt = cur ^ 1;
+    for (int r = gtid; r < N; r += gthreads) {
+      if (!S.active[r]) continue;
+      const int rr = S.role[r];
+      if (rr >= 0 && (rr & 1)) continue;  // absorbed: handled by its partner below
+      bool dirty = false;
+      if (rr >= 0) {
+        const int j = S.pair_j[rr >> 1];
+        S.size[r] += S.size[j];
+        S.parent[j] = r;
+        dirty = true;
+      } else {
+        const int nn = S.nn_idx[r];
+        dirty = nn >= 0 && S.role[nn] >= 0;
+      }
+      if (dirty) S.dirty_list[atomicAdd(&S.counters[nxt], 1)] = r;
+    }
+    grid.sync();
+    for (int p = gtid; p < n_pairs; p += gthreads) {
+      const int i = S.pair_i[p], j = S.pair_j[p];
+      S.active[j] = 0;
+      S.role[i] = -1;
+      S.role[j] = -1;
+    }
+    if (gtid == 0) { S.counters[3] = round + 1; S.counters[4] += n_pairs; }
+    cur = nxt;
+    grid.sync();
+  }
+}
+
+// labels[x] = rank of root(x) among the roots in ascending order (root = smallest member).
+__global__ void __launch_bounds__(1024)
+ahc_labels_kernel(AhcState S, int* __restrict__ labels, int* __restrict__ n_clusters, int* scratch) {
+  __shared__ int part[1024];
+  const int N = S.N, tid = threadIdx.x;
+  const int chunk = (N + 1023) / 1024;
+  const int lo = tid * chunk, hi = min(N, lo + chunk);
+  int cnt = 0;
+  for (int i = lo; i < hi; ++i) cnt += S.active[i] ? 1 : 0;
+  part[tid] = cnt;
+  __syncthreads();
+  // inclusive scan (Hillis-Steele) over 1024 partial counts
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = tid >= o ? part[tid - o] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  int base = part[tid] - cnt;
+  for (int i = lo; i < hi; ++i) {
+    scratch[i] = base;
+    base += S.active[i] ? 1 : 0;
+  }
+  if (tid == 1023) *n_clusters = part[1023];
+  __syncthreads();
+  for (int x = tid; x < N; x += 1024) {
+    int r = x;
+    while (S.parent[r] != r) r = S.parent[r];
+    labels[x] = scratch[r];
+  }
+}
+
+struct Layout {
+  size_t off_D, off_nn_dist, off_ints, total;
+};
+Layout ahc_layout(int N) {
+  Layout L;
+  size_t o = 0;
+  L.off_D = o;
+  o += static_cast<size_t>(N) * N * 8;
+  L.off_nn_dist = o;
+  o += static_cast<size_t>(N) * 8;
+  L.off_ints = o;
+  o += (static_cast<size_t>(N) * 8 + 64) * 4;  // 7 int arrays + scratch + counters
+  L.total = o + 256;
+  return L;
+}
+
+}  // namespace
+
+extern "C" size_t sd_ahc_workspace_bytes(int N) { return N < 1 ? 0 : ahc_layout(N).total; }
+
+extern "C" int sd_ahc_average_f32(const float* dist_dev, int N, double threshold, int32_t* labels_dev,
+                                  int32_t* n_clusters_dev, void* workspace_dev, void* stream) {
+  if (!dist_dev || !labels_dev || !n_clusters_dev || !workspace_dev || N < 1)
+    return fail(SD_ERR_ARG, "sd_ahc_average_f32: bad arguments (N=%d)", N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~uintptr_t(255));
+  const Layout L = ahc_layout(N);
+  AhcState S;
+  S.N = N;
+  S.thr = threshold;  // f64, as sklearn compares the f64 linkage distances with a Python float
+  S.D = reinterpret_cast<double*>(base + L.off_D);
+  S.nn_dist = reinterpret_cast<double*>(base + L.off_nn_dist);
+  int* ip = reinterpret_cast<int*>(base + L.off_ints);
+  S.nn_idx = ip;
+  S.size = ip + N;
+  S.active = ip + 2 * static_cast<size_t>(N);
+  S.parent = ip + 3 * static_cast<size_t>(N);
+  S.role = ip + 4 * static_cast<size_t>(N);
+  S.dirty_list = ip + 5 * static_cast<size_t>(N);
+  S.pair_i = ip + 6 * static_cast<size_t>(N);
+  S.pair_j = S.pair_i + (N / 2 + 1);
+  int* scratch = ip + 7 * static_cast<size_t>(N);
+  S.counters = ip + 8 * static_cast<size_t>(N);
+
+  const int nb = (N + 31) / 32;
+  ahc_init_matrix_kernel<<<dim3(nb, nb), 256, 0, st>>>(dist_dev, N, S.D);
+  ahc_init_state_kernel<<<(N + 255) / 256, 256, 0, st>>>(S);
+  SD_CUDA_OK(cudaGetLastError());
+
+  int dev = 0, sms = 0, occ = 0;
+  SD_CUDA_OK(cudaGetDevice(&dev));
+  SD_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ahc_rounds_kernel, AHC_THREADS, 0));
+  if (occ < 1) return fail(SD_ERR_CUDA, "ahc_rounds_kernel cannot be made resident");
+  if (occ > 4) occ = 4;
+  void* args[] = {&S};
+  SD_CUDA_OK(cudaLaunchCooperativeKernel((void*)ahc_rounds_kernel, dim3(sms * occ), dim3(AHC_THREADS), args, 0, st));
+  ahc_labels_kernel<<<1, 1024, 0, st>>>(S, labels_dev, n_clusters_dev, scratch);
+  SD_CUDA_OK(cudaGetLastError());
+  return SD_OK;
+}

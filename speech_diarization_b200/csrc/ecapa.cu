@@ -1,0 +1,522 @@
+// ecapa.cu — the ECAPA-TDNN (C = 1024) embedding plan: weight repacking, activation
+// workspace, the cached per-shape launch programme, and the forward pass.
+//
+// Replaces the model behind using_ecapa_encoder / EncoderClassifier.encode_batch
+// (/root/reference/speech_encode.py:64-78, ecapa_annote.py:6-22, diar_diag.py:161-170);
+// the arithmetic is speechbrain's ECAPA_TDNN.
+//
+// Data layout in HBM: every activation is f16, channels-last, [B*Tp, C] with
+//   Tp = roundup(T + 2H, 16), H = 4 halo rows on each side of an utterance's T frames
+//   holding the REFLECT padding of the dilated convolutions (max pad = dilation 4).
+// A convolution tap is then a row shift of the TMA box, a 1x1 convolution a plain GEMM,
+// and pointwise layers keep the halo valid for free (they commute with reflection).
+//
+// Forward programme for one batch (all launches on the caller's stream, no host sync):
+//   fbank (2 kernels) -> block0 GEMM(k5) -> 3 x [tdnn1 GEMM, 7 x Res2Net GEMM(k3, fused
+//   "x_{i+1}+y_i"), tdnn2 GEMM, SE mean, SE MLP, SE scale+residual] -> MFA GEMM ->
+//   ASP stats -> context bias -> attention GEMM(tanh) -> pooling GEMM (softmax + weighted
+//   mean/std fused in the epilogue) -> BN-folded FC -> optional L2 norm.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+#include "ecapa_kernels.cuh"
+#include "fbank.cuh"
+#include "gemm_host.cuh"
+#include "sd_status.h"
+
+using namespace sd;
+
+namespace {
+
+constexpr int C1 = 1024;   // trunk channels
+constexpr int C3 = 3072;   // MFA / ASP channels
+constexpr int ATT = 128;   // attention channels
+constexpr int SE = 128;    // squeeze-excitation bottleneck
+constexpr int SUB = 128;   // Res2Net sub-band width (C1 / scale 8)
+constexpr int EMB = 192;
+constexpr int FEAT_P = 128; // 80 mel channels padded to two 64-element K chunks
+constexpr int HALO = 4;
+
+struct TdnnW {       // one TDNNBlock: conv weight (f16, [Cout, taps*CinP]) + folded epilogue constants
+  __half* W = nullptr;
+  float* bias = nullptr;
+  float* scale = nullptr;
+  float* shift = nullptr;
+};
+
+struct BlockW {
+  TdnnW tdnn1, res[7], tdnn2;
+  float *se_w1 = nullptr, *se_b1 = nullptr, *se_w2t = nullptr, *se_b2 = nullptr;
+  int dil = 2;
+};
+
+struct Program {     // launch parameters for one (B, T) shape
+  int B = 0, T = 0, Tp = 0;
+  long rows = 0;
+  GemmParams block0, tdnn1[3], res[3][7], tdnn2[3], mfa, att, pool;
+};
+
+}  // namespace
+
+struct SdEcapaPlan {
+  int max_batch = 0, max_samples = 0;
+  long max_rows = 0;
+  std::vector<void*> allocs;
+  // weights
+  TdnnW w0;
+  BlockW blk[3];
+  TdnnW wmfa, watt;
+  float* Wams = nullptr;  // asp.tdnn weight, mean|std columns [ATT, 2*C3] f32
+  __half* Wa2 = nullptr;  // asp.conv weight [C3, ATT] f16
+  float *Wfc = nullptr, *bfc = nullptr;  // fc with asp_bn folded in, [EMB, 2*C3]
+  // activations
+  __half *feats = nullptr, *x0 = nullptr, *cat = nullptr, *u = nullptr, *v = nullptr, *w = nullptr;
+  __half *s[2] = {nullptr, nullptr}, *h = nullptr, *attn = nullptr;
+  float *raw = nullptr, *se_mean = nullptr, *se_scale = nullptr, *stats = nullptr;
+  float *uttbias = nullptr, *pooled = nullptr;
+  std::map<std::pair<int, int>, Program> programs;
+  Program* last = nullptr;
+};
+
+namespace {
+
+int dev_alloc(SdEcapaPlan* p, void** out, size_t bytes, bool zero) {
+  void* d = nullptr;
+  if (cudaMalloc(&d, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SD_ERR_NOMEM, "cudaMalloc(%zu bytes) failed", bytes);
+  }
+  p->allocs.push_back(d);
+  if (zero) SD_CUDA_OK(cudaMemset(d, 0, bytes));
+  *out = d;
+  return SD_OK;
+}
+
+template <typename T>
+int upload(SdEcapaPlan* p, T** out, const std::vector<T>& host) {
+  void* d = nullptr;
+  SD_TRY(dev_alloc(p, &d, host.size() * sizeof(T), false));
+  SD_CUDA_OK(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<T*>(d);
+  return SD_OK;
+}
+
+struct StateDict {
+  std::unordered_map<std::string, std::pair<const float*, int64_t>> m;
+  int get(const std::string& key, int64_t numel, const float** out) const {
+    auto it = m.find(key);
+    if (it == m.end()) return fail(SD_ERR_MISSING, "state dict has no tensor '%s'", key.c_str());
+    if (it->second.second != numel)
+      return fail(SD_ERR_MISSING, "tensor '%s' has %lld elements, expected %lld", key.c_str(),
+                  (long long)it->second.second, (long long)numel);
+    *out = it->second.first;
+    return SD_OK;
+  }
+};
+
+// speechbrain TDNNBlock "<prefix>.conv.conv.{weight,bias}" + "<prefix>.norm.norm.*" ->
+// f16 weight [cout, taps*cin_p] (tap-major K) and bias / BN scale / BN shift vectors.
+// w_cols restricts the repack to the first w_cols input channels (ASP: x part only).
+int load_tdnn(SdEcapaPlan* p, const StateDict& sd, const std::string& prefix, int cout, int cin,
+              int taps, int cin_p, int w_cols, TdnnW* out) {
+  const float *W, *b, *g, *be, *rm, *rv;
+  SD_TRY(sd.get(prefix + ".conv.conv.weight", (int64_t)cout * cin * taps, &W));
+  SD_TRY(sd.get(prefix + ".conv.conv.bias", cout, &b));
+  SD_TRY(sd.get(prefix + ".norm.norm.weight", cout, &g));
+  SD_TRY(sd.get(prefix + ".norm.norm.bias", cout, &be));
+  SD_TRY(sd.get(prefix + ".norm.norm.running_mean", cout, &rm));
+  SD_TRY(sd.get(prefix + ".norm.norm.running_var", cout, &rv));
+  std::vector<__half> wh((size_t)cout * taps * cin_p, __float2half(0.f));
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < w_cols; ++c)
+      for (int j = 0; j < taps; ++j)
+        wh[((size_t)o * taps + j) * cin_p + c] = __float2half_rn(W[((size_t)o * cin + c) * taps + j]);
+  std::vector<float> bias(b, b + cout), scale(cout), shift(cout);
+  for (int o = 0; o < cout; ++o) {
+    const double sc = (double)g[o] / sqrt((double)rv[o] + 1e-5);
+    scale[o] = (float)sc;
+    shift[o] = (float)((double)be[o] - (double)rm[o] * sc);
+  }
+  SD_TRY(upload(p, &out->W, wh));
+  SD_TRY(upload(p, &out->bias, bias));
+  SD_TRY(upload(p, &out->scale, scale));
+  SD_TRY(upload(p, &out->shift, shift));
+  return SD_OK;
+}
+
+inline int tp_of(int T) { return ((T + 2 * HALO + 15) / 16) * 16; }
+
+// Fills the common fields of a TDNN-epilogue GEMM over `rows` activation rows.
+int setup_tdnn_gemm(GemmParams& P, const __half* A, long rows, int a_cols, int ld_a,
+                    const TdnnW& W, int cout, int k_total, int n_tile, int cin_p, int taps,
+                    int dil, int a_col0, const Program& pr, void* out, int ld_out, int out_col0,
+                    int flags) {
+  init_params(P);
+  SD_TRY(make_tmap_f16(&P.tmapA, A, rows, a_cols, ld_a, BM));
+  SD_TRY(make_tmap_f16(&P.tmapB, W.W, cout, k_total, k_total, n_tile));
+  P.num_m_blocks = (int)((rows + BM - 1) / BM);
+  P.num_n_blocks = cout / n_tile;
+  P.n_tile = n_tile;
+  P.idesc = make_idesc_f16(n_tile, 0);
+  int ki = 0;
+  for (int j = 0; j < taps; ++j)
+    for (int c = 0; c < cin_p / BK; ++c, ++ki) {
+      P.kit[ki].a_col = a_col0 + c * BK;
+      P.kit[ki].a_row_off = (j - taps / 2) * dil;
+      P.kit[ki].b_col = j * cin_p + c * BK;
+      P.kit[ki].slot = 0;
+      P.kit[ki].accum = ki > 0;
+    }
+  P.num_kiters = ki;
+  EpiParams& E = P.epi;
+  E.flags = flags;
+  E.M_rows = (int)rows;
+  E.N_cols = cout;
+  E.Tp = pr.Tp;
+  E.T = pr.T;
+  E.H = HALO;
+  E.out = out;
+  E.ld_out = ld_out;
+  E.out_col_off = out_col0;
+  E.bias = W.bias;
+  E.scale = W.scale;
+  E.shift = W.shift;
+  return SD_OK;
+}
+
+int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
+  auto key = std::make_pair(B, T);
+  auto it = p->programs.find(key);
+  if (it != p->programs.end()) {
+    *out = &it->second;
+    return SD_OK;
+  }
+  if (p->programs.size() > 64) p->programs.clear();
+  Program pr;
+  pr.B = B;
+  pr.T = T;
+  pr.Tp = tp_of(T);
+  pr.rows = (long)B * pr.Tp;
+  const long R = pr.rows;
+  // block0: k = 5 over the 128-padded mel channels
+  SD_TRY(setup_tdnn_gemm(pr.block0, p->feats, R, FEAT_P, FEAT_P, p->w0, C1, 5 * FEAT_P, 256, FEAT_P,
+                         5, 1, 0, pr, p->x0, C1, 0, EF_RELU_BN | EF_REFLECT));
+  for (int b = 0; b < 3; ++b) {
+    const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
+    const int ld_in = b == 0 ? C1 : C3;
+    const BlockW& bw = p->blk[b];
+    // tdnn1: 1x1, also copies sub-band 0 into v (Res2Net passes it through)
+    SD_TRY(setup_tdnn_gemm(pr.tdnn1[b], in, R, C1, ld_in, bw.tdnn1, C1, C1, 256, C1, 1, 1, 0, pr,
+                           p->u, C1, 0, EF_RELU_BN));
+    pr.tdnn1[b].epi.out2 = p->v;
+    pr.tdnn1[b].epi.ld_out2 = C1;
+    pr.tdnn1[b].epi.out2_cols = SUB;
+    // Res2Net chain: y_i = TDNN_i(x_i + y_{i-1}), i = 1..7 (y_0 = x_0 passes through)
+    for (int i = 1; i <= 7; ++i) {
+      const __half* A = i == 1 ? p->u : p->s[i & 1];
+      const int a_cols = i == 1 ? C1 : SUB;
+      const int a_col0 = i == 1 ? SUB : 0;
+      GemmParams& G = pr.res[b][i - 1];
+      SD_TRY(setup_tdnn_gemm(G, A, R, a_cols, a_cols, bw.res[i - 1], SUB, 3 * SUB, 128, SUB, 3,
+                             bw.dil, a_col0, pr, p->v, C1, i * SUB, EF_RELU_BN | EF_REFLECT));
+      if (i < 7) {
+        G.epi.add_src = p->u;
+        G.epi.ld_add = C1;
+        G.epi.add_col_off = (i + 1) * SUB;
+        G.epi.sum_out = p->s[(i + 1) & 1];
+        G.epi.ld_sum = SUB;
+      }
+    }
+    SD_TRY(setup_tdnn_gemm(pr.tdnn2[b], p->v, R, C1, C1, bw.tdnn2, C1, C1, 256, C1, 1, 1, 0, pr,
+                           p->w, C1, 0, EF_RELU_BN));
+  }
+  SD_TRY(setup_tdnn_gemm(pr.mfa, p->cat, R, C3, C3, p->wmfa, C3, C3, 256, C3, 1, 1, 0, pr, p->h, C3,
+                         0, EF_RELU_BN));
+  SD_TRY(setup_tdnn_gemm(pr.att, p->h, R, C3, C3, p->watt, ATT, C3, 128, C3, 1, 1, 0, pr, p->attn,
+                         ATT, 0, EF_RELU_BN | EF_TANH | EF_UTT_BIAS));
+  pr.att.epi.utt_bias = p->uttbias;
+  // pooling GEMM: rows = channels of asp.conv, columns = the Tp rows of one utterance
+  {
+    GemmParams& P = pr.pool;
+    init_params(P);
+    if (pr.Tp > 256)
+      return fail(SD_ERR_UNSUPPORTED,
+                  "windows longer than %d frames (%.2f s) are not supported by the fused pooling "
+                  "kernel yet (T=%d)", 256 - 2 * HALO, (256 - 2 * HALO) * 0.01, T);
+    SD_TRY(make_tmap_f16(&P.tmapA, p->Wa2, C3, ATT, ATT, BM));
+    SD_TRY(make_tmap_f16(&P.tmapB, p->attn, R, ATT, ATT, pr.Tp));
+    P.num_m_blocks = C3 / BM;
+    P.num_n_blocks = B;
+    P.n_tile = pr.Tp;
+    P.idesc = make_idesc_f16(pr.Tp, 0);
+    for (int c = 0; c < ATT / BK; ++c) {
+      P.kit[c].a_col = c * BK;
+      P.kit[c].b_col = c * BK;
+      P.kit[c].accum = c > 0;
+    }
+    P.num_kiters = ATT / BK;
+    P.epi.M_rows = C3;
+    P.epi.N_cols = (int)R;
+    P.epi.Tp = pr.Tp;
+    P.epi.T = T;
+    P.epi.H = HALO;
+    P.epi.h = p->h;
+    P.epi.ld_h = C3;
+    P.epi.gmean = p->stats;   // [B, 2*C3]: mean | std
+    P.epi.ld_gmean = 2 * C3;
+    P.epi.pooled = p->pooled;
+    P.epi.C = C3;
+  }
+  auto ins = p->programs.emplace(key, pr);
+  *out = &ins.first->second;
+  return SD_OK;
+}
+
+int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStream_t st) {
+  const int B = pr.B, T = pr.T, Tp = pr.Tp;
+  const long R = pr.rows;
+  SD_TRY(launch_gemm<EPI_TDNN>(pr.block0, st));
+  for (int b = 0; b < 3; ++b) {
+    const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
+    const int ld_in = b == 0 ? C1 : C3;
+    SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn1[b], st));
+    for (int i = 0; i < 7; ++i) SD_TRY(launch_gemm<EPI_TDNN>(pr.res[b][i], st));
+    SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn2[b], st));
+    time_mean_kernel<<<dim3(C1 / 256, B), 128, 0, st>>>(p->w, C1, Tp, T, HALO, C1, p->se_mean);
+    se_mlp_kernel<<<B, 256, (C1 + SE) * sizeof(float), st>>>(p->se_mean, p->blk[b].se_w1, p->blk[b].se_b1,
+                                                             p->blk[b].se_w2t, p->blk[b].se_b2, C1, SE,
+                                                             p->se_scale);
+    const long vecs = R * (C1 / 8);
+    const int grid = (int)((vecs + 255) / 256 < 148L * 16 ? (vecs + 255) / 256 : 148L * 16);
+    se_apply_kernel<<<grid, 256, 0, st>>>(p->w, C1, p->se_scale, in, ld_in, p->cat + (size_t)b * C1, C3, R,
+                                          Tp, C1);
+    SD_CUDA_OK(cudaGetLastError());
+  }
+  SD_TRY(launch_gemm<EPI_TDNN>(pr.mfa, st));
+  time_mean_std_kernel<<<dim3(C3 / 256, B), 128, 0, st>>>(p->h, C3, Tp, T, HALO, C3, p->stats);
+  // context bias: conv bias + W_mean . mean + W_std . std  (the 2/3 of asp.tdnn that is constant over time)
+  dense_rows_kernel<<<(B + 3) / 4, 256, 0, st>>>(p->Wams, p->watt.bias, p->stats, B, 2 * C3, ATT, p->uttbias);
+  SD_CUDA_OK(cudaGetLastError());
+  SD_TRY(launch_gemm<EPI_TDNN>(pr.att, st));
+  SD_TRY(launch_gemm<EPI_POOL>(pr.pool, st));
+  if (l2_normalize) {
+    dense_rows_kernel<<<(B + 3) / 4, 256, 0, st>>>(p->Wfc, p->bfc, p->pooled, B, 2 * C3, EMB, p->se_mean);
+    l2norm_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->se_mean, B, EMB, 1e-8f, emb);
+  } else {
+    dense_rows_kernel<<<(B + 3) / 4, 256, 0, st>>>(p->Wfc, p->bfc, p->pooled, B, 2 * C3, EMB, emb);
+  }
+  SD_CUDA_OK(cudaGetLastError());
+  p->last = &pr;
+  return SD_OK;
+}
+
+int check_shape(SdEcapaPlan* p, int B, int T) {
+  if (B < 1 || T < 2 * HALO + 2)
+    return fail(SD_ERR_ARG, "ecapa: need B >= 1 and T >= %d frames (B=%d T=%d)", 2 * HALO + 2, B, T);
+  if ((long)B * tp_of(T) > p->max_rows)
+    return fail(SD_ERR_ARG, "ecapa: B=%d x T=%d exceeds the plan's workspace (%ld rows)", B, T, p->max_rows);
+  return SD_OK;
+}
+
+}  // namespace
+
+extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const* tensors,
+                                    const int64_t* numels, int n_tensors, int max_batch,
+                                    int max_samples, SdEcapaPlan** plan_out) {
+  if (!names || !tensors || !numels || !plan_out || n_tensors < 1 || max_batch < 1 || max_samples < 400)
+    return fail(SD_ERR_ARG, "sd_ecapa_plan_create: bad arguments");
+  StateDict sd;
+  for (int i = 0; i < n_tensors; ++i) sd.m[names[i]] = {tensors[i], numels[i]};
+  SdEcapaPlan* p = new SdEcapaPlan;
+  p->max_batch = max_batch;
+  p->max_samples = max_samples;
+  const int maxT = 1 + max_samples / 160;
+  p->max_rows = (long)max_batch * tp_of(maxT);
+  int st = SD_OK;
+  auto body = [&]() -> int {
+    SD_TRY(load_tdnn(p, sd, "blocks.0", C1, 80, 5, FEAT_P, 80, &p->w0));
+    for (int b = 0; b < 3; ++b) {
+      const std::string pre = "blocks." + std::to_string(b + 1);
+      BlockW& bw = p->blk[b];
+      bw.dil = b + 2;
+      SD_TRY(load_tdnn(p, sd, pre + ".tdnn1", C1, C1, 1, C1, C1, &bw.tdnn1));
+      for (int i = 0; i < 7; ++i)
+        SD_TRY(load_tdnn(p, sd, pre + ".res2net_block.blocks." + std::to_string(i), SUB, SUB, 3, SUB, SUB,
+                         &bw.res[i]));
+      SD_TRY(load_tdnn(p, sd, pre + ".tdnn2", C1, C1, 1, C1, C1, &bw.tdnn2));
+      const float *w1, *b1, *w2, *b2;
+      SD_TRY(sd.get(pre + ".se_block.conv1.conv.weight", (int64_t)SE * C1, &w1));
+      SD_TRY(sd.get(pre + ".se_block.conv1.conv.bias", SE, &b1));
+      SD_TRY(sd.get(pre + ".se_block.conv2.conv.weight", (int64_t)C1 * SE, &w2));
+      SD_TRY(sd.get(pre + ".se_block.conv2.conv.bias", C1, &b2));
+      std::vector<float> w2t((size_t)SE * C1);
+      for (int c = 0; c < C1; ++c)
+        for (int j = 0; j < SE; ++j) w2t[(size_t)j * C1 + c] = w2[(size_t)c * SE + j];
+      SD_TRY(upload(p, &bw.se_w1, std::vector<float>(w1, w1 + (size_t)SE * C1)));
+      SD_TRY(upload(p, &bw.se_b1, std::vector<float>(b1, b1 + SE)));
+      SD_TRY(upload(p, &bw.se_w2t, w2t));
+      SD_TRY(upload(p, &bw.se_b2, std::vector<float>(b2, b2 + C1)));
+    }
+    SD_TRY(load_tdnn(p, sd, "mfa", C3, C3, 1, C3, C3, &p->wmfa));
+    // asp.tdnn: [ATT, 3*C3, 1]; columns [0,C3) act on x (tensor cores), [C3, 3*C3) on mean|std
+    SD_TRY(load_tdnn(p, sd, "asp.tdnn", ATT, 3 * C3, 1, C3, C3, &p->watt));
+    {
+      const float* W;
+      SD_TRY(sd.get("asp.tdnn.conv.conv.weight", (int64_t)ATT * 3 * C3, &W));
+      std::vector<float> ms((size_t)ATT * 2 * C3);
+      for (int o = 0; o < ATT; ++o)
+        for (int c = 0; c < 2 * C3; ++c) ms[(size_t)o * 2 * C3 + c] = W[(size_t)o * 3 * C3 + C3 + c];
+      SD_TRY(upload(p, &p->Wams, ms));
+      const float* W2;
+      SD_TRY(sd.get("asp.conv.conv.weight", (int64_t)C3 * ATT, &W2));
+      const float* b2;  // constant over time -> cancels in the softmax; only validated
+      SD_TRY(sd.get("asp.conv.conv.bias", C3, &b2));
+      std::vector<__half> w2h((size_t)C3 * ATT);
+      for (size_t i = 0; i < w2h.size(); ++i) w2h[i] = __float2half_rn(W2[i]);
+      SD_TRY(upload(p, &p->Wa2, w2h));
+    }
+    {
+      // fold asp_bn (eval) into fc: W' = W diag(sc), b' = b + W sh
+      const float *g, *be, *rm, *rv, *W, *b;
+      SD_TRY(sd.get("asp_bn.norm.weight", 2 * C3, &g));
+      SD_TRY(sd.get("asp_bn.norm.bias", 2 * C3, &be));
+      SD_TRY(sd.get("asp_bn.norm.running_mean", 2 * C3, &rm));
+      SD_TRY(sd.get("asp_bn.norm.running_var", 2 * C3, &rv));
+      SD_TRY(sd.get("fc.conv.weight", (int64_t)EMB * 2 * C3, &W));
+      SD_TRY(sd.get("fc.conv.bias", EMB, &b));
+      std::vector<float> wf((size_t)EMB * 2 * C3), bf(EMB);
+      for (int o = 0; o < EMB; ++o) {
+        double acc = b[o];
+        for (int k = 0; k < 2 * C3; ++k) {
+          const double sc = (double)g[k] / sqrt((double)rv[k] + 1e-5);
+          const double sh = (double)be[k] - (double)rm[k] * sc;
+          wf[(size_t)o * 2 * C3 + k] = (float)((double)W[(size_t)o * 2 * C3 + k] * sc);
+          acc += (double)W[(size_t)o * 2 * C3 + k] * sh;
+        }
+        bf[o] = (float)acc;
+      }
+      SD_TRY(upload(p, &p->Wfc, wf));
+      SD_TRY(upload(p, &p->bfc, bf));
+    }
+    // activation workspace (zero-initialised once: padding rows are never written afterwards)
+    const size_t R = (size_t)p->max_rows;
+    SD_TRY(dev_alloc(p, (void**)&p->feats, R * FEAT_P * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->x0, R * C1 * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->cat, R * C3 * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->u, R * C1 * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->v, R * C1 * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->w, R * C1 * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->s[0], R * SUB * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->s[1], R * SUB * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->h, R * C3 * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->attn, R * ATT * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->raw, R * 80 * 4, true));
+    const size_t MB = (size_t)p->max_rows / tp_of(2 * HALO + 2) + 1;  // most utterances any shape can have
+    SD_TRY(dev_alloc(p, (void**)&p->se_mean, MB * C1 * 4, true));
+    SD_TRY(dev_alloc(p, (void**)&p->se_scale, MB * C1 * 4, true));
+    SD_TRY(dev_alloc(p, (void**)&p->stats, MB * 2 * C3 * 4, true));
+    SD_TRY(dev_alloc(p, (void**)&p->uttbias, MB * ATT * 4, true));
+    SD_TRY(dev_alloc(p, (void**)&p->pooled, MB * 2 * C3 * 4, true));
+    SD_CUDA_OK(cudaDeviceSynchronize());
+    return SD_OK;
+  };
+  st = body();
+  if (st != SD_OK) {
+    for (void* d : p->allocs) cudaFree(d);
+    delete p;
+    return st;
+  }
+  *plan_out = p;
+  return SD_OK;
+}
+
+extern "C" int sd_ecapa_plan_destroy(SdEcapaPlan* p) {
+  if (!p) return SD_OK;
+  cudaDeviceSynchronize();
+  for (void* d : p->allocs) cudaFree(d);
+  delete p;
+  return SD_OK;
+}
+
+extern "C" int sd_ecapa_embed(SdEcapaPlan* p, const float* wav_dev, long wav_stride, int B,
+                              int n_samples, int l2_normalize, float* emb_dev, void* stream) {
+  if (!p || !wav_dev || !emb_dev) return fail(SD_ERR_ARG, "sd_ecapa_embed: NULL argument");
+  if (n_samples < 400) return fail(SD_ERR_ARG, "sd_ecapa_embed: n_samples=%d < 400", n_samples);
+  const int T = 1 + n_samples / 160;
+  SD_TRY(check_shape(p, B, T));
+  Program* pr = nullptr;
+  SD_TRY(build_program(p, B, T, &pr));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SD_TRY(fbank_launch(wav_dev, wav_stride, B, n_samples, SD_FBANK_SPEECHBRAIN, 1, p->raw, nullptr,
+                      p->feats, pr->Tp, HALO, st));
+  return run_trunk(p, *pr, l2_normalize, emb_dev, st);
+}
+
+extern "C" int sd_ecapa_forward_feats(SdEcapaPlan* p, const float* feats_dev, int B, int T,
+                                      int l2_normalize, float* emb_dev, void* stream) {
+  if (!p || !feats_dev || !emb_dev) return fail(SD_ERR_ARG, "sd_ecapa_forward_feats: NULL argument");
+  SD_TRY(check_shape(p, B, T));
+  Program* pr = nullptr;
+  SD_TRY(build_program(p, B, T, &pr));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SD_TRY(feats_to_padded_f16(feats_dev, B, T, p->feats, pr->Tp, HALO, st));
+  return run_trunk(p, *pr, l2_normalize, emb_dev, st);
+}
+
+extern "C" int sd_ecapa_debug_fetch(SdEcapaPlan* p, const char* name, float* out_dev, int* C_out,
+                                    void* stream) {
+  if (!p || !name || !out_dev || !p->last) return fail(SD_ERR_ARG, "sd_ecapa_debug_fetch: no forward yet");
+  const Program& pr = *p->last;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const std::string n(name);
+  const __half* src = nullptr;
+  int ld = 0, off = 0, C = 0;
+  if (n == "feats") { src = p->feats; ld = FEAT_P; C = 80; }
+  else if (n == "block0") { src = p->x0; ld = C1; C = C1; }
+  else if (n == "b1.out") { src = p->cat; ld = C3; C = C1; }
+  else if (n == "b2.out") { src = p->cat; ld = C3; off = C1; C = C1; }
+  else if (n == "b3.out") { src = p->cat; ld = C3; off = 2 * C1; C = C1; }
+  else if (n == "b3.tdnn1") { src = p->u; ld = C1; C = C1; }
+  else if (n == "b3.res2net") { src = p->v; ld = C1; C = C1; }
+  else if (n == "b3.tdnn2") { src = p->w; ld = C1; C = C1; }
+  else if (n == "mfa") { src = p->h; ld = C3; C = C3; }
+  else if (n == "asp.attn") { src = p->attn; ld = ATT; C = ATT; }
+  if (src) {
+    const long total = (long)pr.B * pr.T * C;
+    fetch_interior_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(
+        src, ld, off, pr.Tp, pr.T, HALO, C, total, out_dev);
+    SD_CUDA_OK(cudaGetLastError());
+    if (C_out) *C_out = C;
+    return SD_OK;
+  }
+  const float* fsrc = nullptr;
+  if (n == "b3.se") { fsrc = p->se_scale; C = C1; }
+  else if (n == "asp.stats") { fsrc = p->stats; C = 2 * C3; }
+  else if (n == "asp.uttbias") { fsrc = p->uttbias; C = ATT; }
+  else if (n == "pooled") { fsrc = p->pooled; C = 2 * C3; }
+  if (!fsrc) return fail(SD_ERR_ARG, "sd_ecapa_debug_fetch: unknown tensor '%s'", name);
+  SD_CUDA_OK(cudaMemcpyAsync(out_dev, fsrc, (size_t)pr.B * C * 4, cudaMemcpyDeviceToDevice, st));
+  if (C_out) *C_out = C;
+  return SD_OK;
+}
+
+extern "C" double sd_ecapa_flops_per_window(int T) {
+  // MACs per frame / per utterance of the contractions issued (ASP decomposed)
+  const double per_frame = 80.0 * 5 * C1 + 3.0 * (2.0 * C1 * C1 + 7.0 * 3 * SUB * SUB) +
+                           (double)C3 * C3 + (double)C3 * ATT + (double)ATT * C3;
+  const double per_utt = 3.0 * 2 * C1 * SE + 2.0 * C3 * ATT + 2.0 * C3 * EMB;
+  return 2.0 * (per_frame * T + per_utt);
+}
+
+extern "C" int sd_l2norm_f32(const float* x_dev, int N, int D, float eps, float* out_dev, void* stream) {
+  if (!x_dev || !out_dev || N < 0 || D < 1) return fail(SD_ERR_ARG, "sd_l2norm_f32: bad arguments");
+  if (N == 0) return SD_OK;
+  l2norm_rows_kernel<<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, N, D, eps, out_dev);
+  SD_CUDA_OK(cudaGetLastError());
+  return SD_OK;
+}

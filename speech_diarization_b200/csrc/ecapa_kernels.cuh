@@ -1,0 +1,227 @@
+// ecapa_kernels.cuh — the non-GEMM kernels of the ECAPA-TDNN trunk:
+// squeeze-excitation (time mean -> 2-layer MLP -> scale + residual), the global
+// statistics of attentive pooling, and the small dense layers that act once per
+// utterance.  All are bandwidth-bound reductions over the f16 channels-last
+// activation tensors [B*Tp, C] written by the GEMM epilogues (gemm_tc.cuh).
+//
+// Reference arithmetic: speechbrain SEBlock / AttentiveStatisticsPooling /
+// asp_bn + fc inside ECAPA_TDNN.forward, reached from speech_encode.py:77 and
+// ecapa_annote.py:22.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include "sd_ptx.cuh"
+
+namespace sd {
+
+// mean over the T interior frames of utterance b, per channel.
+// x: [B*Tp, ld] f16.  grid (C/256, B), block 128: one half2 (2 channels) per thread.
+__global__ void __launch_bounds__(128)
+time_mean_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H, int C,
+                 float* __restrict__ mean_out /*[B, C]*/) {
+  const int b = blockIdx.y;
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
+  if (c >= C) return;
+  const __half2* p = reinterpret_cast<const __half2*>(x + (static_cast<size_t>(b) * Tp + H) * ld + c);
+  const size_t step = static_cast<size_t>(ld) / 2;
+  float s0 = 0.f, s1 = 0.f;
+  int t = 0;
+  for (; t + 8 <= T; t += 8) {
+    __half2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[(t + j) * step];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 f = __half22float2(v[j]);
+      s0 += f.x;
+      s1 += f.y;
+    }
+  }
+  for (; t < T; ++t) {
+    const float2 f = __half22float2(p[t * step]);
+    s0 += f.x;
+    s1 += f.y;
+  }
+  const float inv = 1.0f / static_cast<float>(T);
+  mean_out[static_cast<size_t>(b) * C + c] = s0 * inv;
+  mean_out[static_cast<size_t>(b) * C + c + 1] = s1 * inv;
+}
+
+// mean and std (uniform weights 1/T, eps 1e-12) over interior frames; stats[b] = [mean(C), std(C)].
+__global__ void __launch_bounds__(128)
+time_mean_std_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H, int C,
+                     float* __restrict__ stats /*[B, 2C]*/) {
+  const int b = blockIdx.y;
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
+  if (c >= C) return;
+  const __half2* p = reinterpret_cast<const __half2*>(x + (static_cast<size_t>(b) * Tp + H) * ld + c);
+  const size_t step = static_cast<size_t>(ld) / 2;
+  float s0 = 0.f, s1 = 0.f;
+  int t = 0;
+  for (; t + 8 <= T; t += 8) {
+    __half2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[(t + j) * step];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 f = __half22float2(v[j]);
+      s0 += f.x;
+      s1 += f.y;
+    }
+  }
+  for (; t < T; ++t) {
+    const float2 f = __half22float2(p[t * step]);
+    s0 += f.x;
+    s1 += f.y;
+  }
+  const float inv = 1.0f / static_cast<float>(T);
+  const float m0 = s0 * inv, m1 = s1 * inv;
+  float q0 = 0.f, q1 = 0.f;
+  t = 0;
+  for (; t + 8 <= T; t += 8) {
+    __half2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[(t + j) * step];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 f = __half22float2(v[j]);
+      q0 = fmaf(f.x - m0, f.x - m0, q0);
+      q1 = fmaf(f.y - m1, f.y - m1, q1);
+    }
+  }
+  for (; t < T; ++t) {
+    const float2 f = __half22float2(p[t * step]);
+    q0 = fmaf(f.x - m0, f.x - m0, q0);
+    q1 = fmaf(f.y - m1, f.y - m1, q1);
+  }
+  float* o = stats + static_cast<size_t>(b) * 2 * C;
+  o[c] = m0;
+  o[c + 1] = m1;
+  o[C + c] = sqrtf(fmaxf(q0 * inv, 1e-12f));
+  o[C + c + 1] = sqrtf(fmaxf(q1 * inv, 1e-12f));
+}
+
+// SE excitation: scale[b] = sigmoid(W2 relu(W1 mean[b] + b1) + b2).
+// W1 [S][C] row-major, W2t [S][C] (= conv2 weight transposed).  grid B, block 256.
+__global__ void __launch_bounds__(256)
+se_mlp_kernel(const float* __restrict__ mean, const float* __restrict__ W1,
+              const float* __restrict__ b1, const float* __restrict__ W2t,
+              const float* __restrict__ b2, int C, int S, float* __restrict__ scale) {
+  extern __shared__ float sm[];
+  float* m = sm;       // [C]
+  float* hid = sm + C; // [S]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < C; i += 256) m[i] = mean[static_cast<size_t>(b) * C + i];
+  __syncthreads();
+  for (int j = warp; j < S; j += 8) {
+    const float4* w = reinterpret_cast<const float4*>(W1 + static_cast<size_t>(j) * C);
+    float acc = 0.f;
+    for (int i = lane; i < C / 4; i += 32) {
+      const float4 wv = __ldg(w + i);
+      acc += wv.x * m[4 * i] + wv.y * m[4 * i + 1] + wv.z * m[4 * i + 2] + wv.w * m[4 * i + 3];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) hid[j] = fmaxf(acc + b1[j], 0.f);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    float acc = b2[c];
+    for (int j = 0; j < S; ++j) acc = fmaf(hid[j], __ldg(W2t + static_cast<size_t>(j) * C + c), acc);
+    scale[static_cast<size_t>(b) * C + c] = 1.0f / (1.0f + __expf(-acc));
+  }
+}
+
+// out[r, c] = w[r, c] * scale[b(r), c] + res[r, c]  over ALL rows (halo rows included, so the
+// reflect halo stays valid); 8 channels per thread.
+__global__ void __launch_bounds__(256)
+se_apply_kernel(const __half* __restrict__ w, int ld_w, const float* __restrict__ scale,
+                const __half* __restrict__ res, int ld_res, __half* __restrict__ out, int ld_out,
+                long rows, int Tp, int C) {
+  const int vec_per_row = C / 8;
+  const long total = rows * vec_per_row;
+  for (long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * 256) {
+    const long r = i / vec_per_row;
+    const int c = static_cast<int>(i - r * vec_per_row) * 8;
+    const int b = static_cast<int>(r / Tp);
+    const uint4 wv = *reinterpret_cast<const uint4*>(w + r * ld_w + c);
+    const uint4 rv = *reinterpret_cast<const uint4*>(res + r * ld_res + c);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + static_cast<size_t>(b) * C + c);
+    const float4 s1 = *reinterpret_cast<const float4*>(scale + static_cast<size_t>(b) * C + c + 4);
+    const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    uint4 ov;
+    __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = __half22float2(wh[e]);
+      const float2 q = __half22float2(rh[e]);
+      oh[e] = __floats2half2_rn(fmaf(a.x, sc[2 * e], q.x), fmaf(a.y, sc[2 * e + 1], q.y));
+    }
+    *reinterpret_cast<uint4*>(out + r * ld_out + c) = ov;
+  }
+}
+
+// Y[b, o] = bias[o] + sum_k W[o, k] * X[b, k]   (per-utterance dense layer, f32).
+// One CTA handles UB = 4 utterances so each weight row is read once per 4 outputs rows.
+// grid ceil(B/4), block 256 (8 warps; warp w owns outputs w, w+8, ...).  K % 4 == 0.
+__global__ void __launch_bounds__(256)
+dense_rows_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                  const float* __restrict__ X, int B, int K, int O, float* __restrict__ Y) {
+  const int b0 = blockIdx.x * 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb = min(4, B - b0);
+  const float4* x[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    x[u] = reinterpret_cast<const float4*>(X + static_cast<size_t>(b0 + (u < nb ? u : 0)) * K);
+  for (int o = warp; o < O; o += 8) {
+    const float4* w = reinterpret_cast<const float4*>(W + static_cast<size_t>(o) * K);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < K / 4; i += 32) {
+      const float4 wv = __ldg(w + i);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 xv = __ldg(x[u] + i);
+        acc[u] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
+    if (lane == 0) {
+      const float bo = bias ? bias[o] : 0.f;
+      for (int u = 0; u < nb; ++u) Y[static_cast<size_t>(b0 + u) * O + o] = acc[u] + bo;
+    }
+  }
+}
+
+// out[i,:] = x[i,:] / (||x[i,:]|| + eps); one warp per row.
+__global__ void __launch_bounds__(256)
+l2norm_rows_kernel(const float* __restrict__ x, int N, int D, float eps, float* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* p = x + static_cast<size_t>(row) * D;
+  float s = 0.f;
+  for (int i = lane; i < D; i += 32) s = fmaf(p[i], p[i], s);
+  s = warp_sum(s);
+  const float inv = 1.0f / (sqrtf(s) + eps);
+  for (int i = lane; i < D; i += 32) out[static_cast<size_t>(row) * D + i] = p[i] * inv;
+}
+
+// test hook: interior frames of a padded f16 tensor -> f32 [B, T, C]
+__global__ void __launch_bounds__(256)
+fetch_interior_kernel(const __half* __restrict__ x, int ld, int col_off, int Tp, int T, int H,
+                      int C, long total, float* __restrict__ out) {
+  for (long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * 256) {
+    const int c = static_cast<int>(i % C);
+    const long bt = i / C;
+    const int t = static_cast<int>(bt % T);
+    const long b = bt / T;
+    out[i] = __half2float(x[(b * Tp + H + t) * ld + col_off + c]);
+  }
+}
+
+}  // namespace sd

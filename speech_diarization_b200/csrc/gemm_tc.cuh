@@ -85,7 +85,8 @@ struct EpiParams {
   // EPI_POOL: h activations, global mean, pooled output [B, 2*C]
   const __half* h;
   int ld_h;
-  const float* gmean;  // [B, C]
+  const float* gmean;  // [B, ld_gmean], first C entries of a row = mean
+  int ld_gmean;
   float* pooled;       // [B, 2*C]: mean then std
   int C;
   // EPI_AFF
@@ -266,7 +267,7 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
     }
   }
   // pass 2: softmax-weighted first/second moments about the global mean g
-  const float g = chv ? E.gmean[static_cast<size_t>(b) * E.C + ch] : 0.f;
+  const float g = chv ? E.gmean[static_cast<size_t>(b) * E.ld_gmean + ch] : 0.f;
   const __half* hcol = E.h + static_cast<size_t>(b) * E.Tp * E.ld_h + (chv ? ch : 0);
   float se = 0.f, s1 = 0.f, s2 = 0.f;
   for (int c0 = 0; c0 < P.n_tile; c0 += 16) {

@@ -1,0 +1,153 @@
+"""Generates tests/golden/*.npz by importing and running the REFERENCE modules
+themselves (/root/reference, read-only) in this CPU-only container.
+
+The reference imports third-party packages that are not installed here
+(onnxruntime, speechbrain, librosa, pyloudnorm, hdbscan, soundfile, matplotlib,
+pyannote); none of them is touched by the functions exercised below, so they are
+replaced by empty stub modules for the import to succeed.  ``fbank_batch``
+hard-codes 'cuda' (SURVEY defect D6): ``Tensor.cuda`` / ``Module.to('cuda')`` are
+patched to no-ops so the reference's own torchaudio arithmetic runs on CPU.
+
+Run:  python tests/golden/make_golden.py        (needs /root/reference; not run on the GPU box)
+"""
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+class _Any:
+    def __init__(self, *a, **k): pass
+    def __call__(self, *a, **k): return self
+    def __getattr__(self, k): return _Any()
+
+
+for name in ["onnxruntime", "librosa", "librosa.util", "librosa.effects", "pyloudnorm", "hdbscan", "soundfile",
+             "matplotlib", "matplotlib.pyplot", "speechbrain", "speechbrain.inference",
+             "speechbrain.inference.classifiers", "speechbrain.inference.speaker"]:
+    _stub(name)
+sys.modules["speechbrain.inference.classifiers"].EncoderClassifier = _Any
+sys.modules["speechbrain.inference.speaker"].EncoderClassifier = _Any
+sys.modules["hdbscan"].HDBSCAN = _Any
+sys.modules["onnxruntime"].InferenceSession = _Any
+
+# 'cuda' -> CPU
+torch.Tensor.cuda = lambda self, *a, **k: self
+_orig_to = torch.nn.Module.to
+torch.nn.Module.to = lambda self, *a, **k: self if (a and a[0] == "cuda") else _orig_to(self, *a, **k)
+
+sys.path.insert(0, REF)
+import speech_encode as ref_se          # noqa: E402
+import diar_diag as ref_dd              # noqa: E402
+
+# vad.py imports librosa at module level and uses librosa.util.frame; give the stub the
+# documented semantics (frames along the last axis, no padding) so vad.frame_audio runs.
+def _librosa_frame(y, frame_length, hop_length):
+    n = 1 + (len(y) - frame_length) // hop_length
+    idx = np.arange(frame_length)[:, None] + hop_length * np.arange(n)[None, :]
+    return y[idx]                        # [frame_length, n]; vad.py:14-16 transposes
+sys.modules["librosa"].util = sys.modules["librosa.util"]
+sys.modules["librosa.util"].frame = _librosa_frame
+import anti_stick_diarize as ref_as     # noqa: E402  (imports vad -> numba, scipy)
+
+
+def synth_wave(B, n, seed):
+    """Harmonic stacks + noise, roughly speech-like level; f32 in [-1, 1]."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / 16000.0
+    out = np.zeros((B, n), np.float32)
+    for b in range(B):
+        f0 = 110.0 * (1 + 0.5 * b)
+        sig = sum(np.sin(2 * np.pi * f0 * h * t + rng.uniform(0, 6.28)) / h for h in range(1, 12))
+        sig = 0.1 * sig + 0.003 * rng.standard_normal(n)
+        if b % 2 == 1:
+            sig[n // 2:] *= 0.05          # a quiet half, exercises the log floor
+        out[b] = sig.astype(np.float32)
+    return out
+
+
+def synth_embeddings(N, K, sigma, seed, D=192):
+    rng = np.random.default_rng(seed)
+    c = rng.standard_normal((K, D))
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    lab = rng.integers(0, K, N)
+    X = (c[lab] + sigma * rng.standard_normal((N, D))).astype(np.float32)
+    return X, lab
+
+
+def main():
+    # ---- a3: fbank_batch (speech_encode.py:10-38), the reference function itself
+    for tag, (B, n, seed) in {"short": (3, 4000, 1), "win15": (2, 24000, 2)}.items():
+        w = synth_wave(B, n, seed)
+        np.savez_compressed(os.path.join(OUT, f"fbank_ref_{tag}.npz"), wav_seed=seed, B=B, n=n,
+                            wav=w.astype(np.float16) if False else w,
+                            cmn=ref_se.fbank_batch(w, mean_nor=True),
+                            raw=ref_se.fbank_batch(w, mean_nor=False))
+    # ---- a8: cluster_embeddings "agglo" (diar_diag.py:213-229), the reference function itself
+    cases = {}
+    for tag, (N, K, sigma, seed) in {"clean": (400, 5, 0.02, 3), "noisy": (300, 6, 0.05, 4),
+                                     "tiny": (7, 2, 0.02, 5)}.items():
+        X, lab = synth_embeddings(N, K, sigma, seed)
+        cases[f"{tag}_X"] = X
+        cases[f"{tag}_true"] = lab
+        cases[f"{tag}_labels"] = ref_dd.cluster_embeddings(X, method="agglo", cos_thr=0.68)
+        cases[f"{tag}_labels_thr05"] = ref_dd.cluster_embeddings(X, method="agglo", cos_thr=0.5)
+    np.savez_compressed(os.path.join(OUT, "cluster_ref.npz"), **cases)
+    # ---- a1: frame_audio (vad.py:9-16 and diar_diag.py:48-56)
+    y = np.arange(5000, dtype=np.float32)
+    fr_v = ref_as.frame_audio(y, 16000, win_ms=30.0, hop_ms=10.0)
+    fr_d, hop = ref_dd.frame_audio(y, 16000, 30.0, 10.0)
+    assert np.array_equal(fr_v, fr_d)
+    fr2 = ref_as.frame_audio(y, 16000, win_ms=100.0, hop_ms=37.5)
+    # ---- a2/a9: windows, labels -> segments, merge (anti_stick_diarize.py:352-386,464-475)
+    Seg = ref_as.Segment
+    mask = [Seg(0.2, 1.7), Seg(2.5, 4.05), Seg(5.0, 5.4)]
+    ylen = 6 * 16000 + 123
+    ws, vi = ref_as._get_speech_windows(np.zeros(ylen, np.float32), 16000, mask, 16000, 1600)
+    rng = np.random.default_rng(6)
+    wl = np.repeat(rng.integers(0, 3, 12), 5)[: len(vi)]
+    segs = ref_as._labels_to_segments(ws, vi, wl, 16000, ylen / 16000)
+    merged = ref_as.merge_adjacent(segs, gap=0.05)
+    # ---- a2: embed_segments batching/padding (anti_stick_diarize.py:130-172) with a recording encoder
+    calls = []
+    def fake_encode(batch):
+        calls.append(batch.copy())
+        return np.tile(batch.sum(axis=1, keepdims=True), (1, 192)).astype(np.float32)
+    ref_as.ecapa_encode_batch = fake_encode
+    ya = (np.arange(3 * 16000) % 977).astype(np.float32) / 977.0
+    esegs = [Seg(0.0, 0.3), Seg(0.5, 1.6), Seg(1.7, 1.9), Seg(2.0, 2.95), Seg(2.9, 3.0)]
+    embs = ref_as.embed_segments(ya, 16000, esegs, batch_size=2)
+    np.savez_compressed(
+        os.path.join(OUT, "windows_ref.npz"),
+        frames_30_10=fr_v, frames_100_37=fr2,
+        mask=np.array([[s.start, s.end] for s in mask]), ylen=ylen,
+        window_starts=ws, valid_indices=vi, window_labels=wl,
+        segs=np.array([[s.start, s.end, s.spk] for s in segs]),
+        merged=np.array([[s.start, s.end, s.spk] for s in merged]),
+        embed_y=ya, embed_segs=np.array([[s.start, s.end] for s in esegs]),
+        embed_shapes=np.array([c.shape for c in calls]),
+        embed_sums=np.concatenate([c.sum(axis=1) for c in calls]),
+        embed_out=embs,
+        empty_out_shape=np.array(ref_as.embed_segments(ya, 16000, []).shape),
+    )
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            p = os.path.join(OUT, f)
+            print(f, os.path.getsize(p), hashlib.sha256(open(p, "rb").read()).hexdigest()[:12])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,165 @@
+"""CPU tests: the oracle is pinned against golden vectors produced by the REFERENCE's own
+functions (tests/golden/make_golden.py), and the host-side (numpy) logic of the product
+package reproduces the reference's window / segment / RTTM conventions bit-exactly."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, synth_emb
+from oracle import cluster_oracle as co
+from oracle import ecapa_oracle as eo
+from oracle import fbank_oracle as fo
+
+
+# ------------------------------------------------------------------ oracle vs reference goldens
+@pytest.mark.parametrize("tag", ["short", "win15"])
+def test_fbank_oracle_matches_reference_fbank_batch(tag):
+    g = golden(f"fbank_ref_{tag}.npz")
+    np.testing.assert_array_equal(fo.fbank_batch(g["wav"], mean_nor=True), g["cmn"])
+    np.testing.assert_array_equal(fo.fbank_batch(g["wav"], mean_nor=False), g["raw"])
+    assert g["cmn"].shape == (int(g["B"]), 1 + int(g["n"]) // 160, 80)
+
+
+@pytest.mark.parametrize("tag", ["clean", "noisy", "tiny"])
+def test_cluster_oracle_matches_reference_cluster_embeddings(tag):
+    g = golden("cluster_ref.npz")
+    X = g[f"{tag}_X"]
+    np.testing.assert_array_equal(co.cluster_embeddings(X, "agglo", 0.68), g[f"{tag}_labels"])
+    np.testing.assert_array_equal(co.cluster_embeddings(X, "agglo", 0.5), g[f"{tag}_labels_thr05"])
+    if tag == "clean":
+        assert co.same_partition(g["clean_labels"], g["clean_true"])
+
+
+def test_cluster_oracle_rejects_unknown_method():
+    with pytest.raises(ValueError):
+        co.cluster_embeddings(np.zeros((4, 192), np.float32), "kmeans")
+
+
+def test_window_helpers_match_reference():
+    g = golden("windows_ref.npz")
+    y = np.arange(5000, dtype=np.float32)
+    np.testing.assert_array_equal(co.frame_audio(y, 16000, 30.0, 10.0), g["frames_30_10"])
+    np.testing.assert_array_equal(co.frame_audio(y, 16000, 100.0, 37.5), g["frames_100_37"])
+    mask = [co.Segment(a, b) for a, b in g["mask"]]
+    ws, vi = co.get_speech_windows(int(g["ylen"]), 16000, mask, 16000, 1600)
+    np.testing.assert_array_equal(ws, g["window_starts"])
+    np.testing.assert_array_equal(vi, g["valid_indices"])
+    segs = co.labels_to_segments(ws, vi, g["window_labels"], 16000, int(g["ylen"]) / 16000)
+    np.testing.assert_array_equal(np.array([[s.start, s.end, s.spk] for s in segs]), g["segs"])
+    merged = co.merge_adjacent(segs, 0.05)
+    np.testing.assert_array_equal(np.array([[s.start, s.end, s.spk] for s in merged]), g["merged"])
+
+
+# ------------------------------------------------------------------------- ECAPA oracle (unpinned)
+def test_ecapa_oracle_topology():
+    m = eo.ECAPA_TDNN()
+    assert eo.count_params(m) == 20_767_552
+    keys = set(m.state_dict())
+    for k in ["blocks.0.conv.conv.weight", "blocks.1.tdnn1.norm.norm.running_var",
+              "blocks.2.res2net_block.blocks.6.conv.conv.bias", "blocks.3.se_block.conv2.conv.weight",
+              "mfa.conv.conv.weight", "asp.tdnn.conv.conv.weight", "asp.conv.conv.bias",
+              "asp_bn.norm.running_mean", "fc.conv.weight"]:
+        assert k in keys, k
+    assert m.state_dict()["asp.tdnn.conv.conv.weight"].shape == (128, 9216, 1)
+    with torch.inference_mode():
+        out = m.eval()(eo.synth_features(2, 37, 0))
+    assert out.shape == (2, 1, 192)
+
+
+def test_speechbrain_fbank_oracle_shape_and_norm():
+    w = torch.randn(3, 24000) * 0.1
+    f = eo.fbank_speechbrain(w)
+    assert f.shape == (3, 151, 80)
+    assert float(f.mean(dim=1).abs().max()) < 1e-4           # sentence mean normalisation
+    raw = eo.fbank_speechbrain(w, mean_norm=False)
+    assert float((raw.amax(dim=(1, 2)) - raw.amin(dim=(1, 2))).max()) <= 80.0 + 1e-3   # top_db
+
+
+# ----------------------------------------------------------- product host logic (numpy, no GPU)
+def test_product_frame_audio_is_view_and_matches_reference():
+    from speech_diarization_b200 import vad, diar_diag
+    g = golden("windows_ref.npz")
+    y = np.arange(5000, dtype=np.float32)
+    fr = vad.frame_audio(y, 16000, 30.0, 10.0)
+    np.testing.assert_array_equal(fr, g["frames_30_10"])
+    assert fr.base is not None and fr.strides == (160 * 4, 4)      # no copy
+    np.testing.assert_array_equal(vad.frame_audio(y, 16000, 100.0, 37.5), g["frames_100_37"])
+    fr2, hop = diar_diag.frame_audio(y, 16000, 30.0, 10.0)
+    np.testing.assert_array_equal(fr2, g["frames_30_10"])
+    assert hop == 160
+    short, _ = diar_diag.frame_audio(np.ones(100, np.float32), 16000)       # pads to one window
+    assert short.shape == (1, 480) and short[0, 100:].sum() == 0
+    with pytest.raises(ValueError):
+        vad.frame_audio(np.ones(100, np.float32), 16000)
+
+
+def test_product_overlap_span_detection():
+    from speech_diarization_b200 import vad, speech_encode
+    y = np.random.default_rng(0).standard_normal(100000).astype(np.float32)
+    fr = vad.frame_audio(y, 16000, 1500.0, 750.0)
+    span, hop = speech_encode._overlap_span(fr)
+    assert hop == 12000 and span.shape[0] == (fr.shape[0] - 1) * 12000 + 24000
+    np.testing.assert_array_equal(span, y[: span.shape[0]])
+    assert speech_encode._overlap_span(np.ascontiguousarray(fr)) is None
+
+
+def test_product_segment_logic_matches_reference():
+    from speech_diarization_b200 import anti_stick_diarize as asd
+    g = golden("windows_ref.npz")
+    mask = [asd.Segment(a, b) for a, b in g["mask"]]
+    ws, vi = asd._get_speech_windows(np.zeros(int(g["ylen"]), np.float32), 16000, mask, 16000, 1600)
+    np.testing.assert_array_equal(ws, g["window_starts"])
+    np.testing.assert_array_equal(vi, g["valid_indices"])
+    segs = asd._labels_to_segments(ws, vi, g["window_labels"], 16000, int(g["ylen"]) / 16000)
+    np.testing.assert_array_equal(np.array([[s.start, s.end, s.spk] for s in segs]), g["segs"])
+    merged = asd.merge_adjacent(segs, 0.05)
+    np.testing.assert_array_equal(np.array([[s.start, s.end, s.spk] for s in merged]), g["merged"])
+    assert asd.merge_adjacent([]) == []
+
+
+def test_product_embed_segments_batching_matches_reference(monkeypatch):
+    from speech_diarization_b200 import anti_stick_diarize as asd
+    g = golden("windows_ref.npz")
+    calls = []
+
+    def fake(batch):
+        calls.append(batch.copy())
+        return np.tile(batch.sum(axis=1, keepdims=True), (1, 192)).astype(np.float32)
+
+    monkeypatch.setattr(asd, "ecapa_encode_batch", fake)
+    segs = [asd.Segment(a, b) for a, b in g["embed_segs"]]
+    out = asd.embed_segments(g["embed_y"], 16000, segs, batch_size=2)
+    np.testing.assert_array_equal(np.array([c.shape for c in calls]), g["embed_shapes"])
+    np.testing.assert_array_equal(np.concatenate([c.sum(axis=1) for c in calls]), g["embed_sums"])
+    np.testing.assert_array_equal(out, g["embed_out"])
+    empty = asd.embed_segments(g["embed_y"], 16000, [])
+    assert empty.shape == tuple(g["empty_out_shape"]) == (0, 192) and empty.dtype == np.float32
+
+
+def test_product_rttm_format(tmp_path):
+    from speech_diarization_b200 import diarization_baseline as db, anti_stick_diarize as asd
+    segs = [asd.Segment(1.5, 3.25, 1), asd.Segment(0.0, 1.5, 0)]
+    tup = db.segments_to_tuples(segs)
+    assert tup == [(0.0, 1.5, "SPEAKER_00"), (1.5, 3.25, "SPEAKER_01")]
+    p = tmp_path / "clip.rttm"
+    db.write_rttm(tup, p)
+    assert p.read_text().splitlines() == [
+        "SPEAKER clip 1 0.000 1.500 <NA> <NA> SPEAKER_00 <NA> <NA>",
+        "SPEAKER clip 1 1.500 1.750 <NA> <NA> SPEAKER_01 <NA> <NA>"]
+    assert db.rttm_lines(tup, "clip") == co.rttm_lines(tup, "clip")
+
+
+def test_product_cluster_embeddings_error_behaviour():
+    from speech_diarization_b200 import diar_diag
+    with pytest.raises(ValueError):
+        diar_diag.cluster_embeddings(np.zeros((4, 192), np.float32), method="kmeans")
+    with pytest.raises(NotImplementedError):
+        diar_diag.cluster_embeddings(np.zeros((4, 192), np.float32))       # default "hdbscan": out of scope
+
+
+def test_product_fails_loudly_without_gpu():
+    from speech_diarization_b200 import _lib, speech_encode
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.SdError):
+        speech_encode.fbank_batch(np.zeros((1, 4000), np.float32))
