@@ -42,6 +42,8 @@ extern "C" {
 int sd_version(void);
 const char* sd_status_string(int status);
 const char* sd_last_error(void);
+/* Number of CUDA kernels this library has launched since it was loaded. */
+long sd_launch_count(void);
 
 /* ------------------------------------------------------------------ fbank ---
  * Number of frames a centre-padded STFT (n_fft = win = 400, hop = 160) yields:
@@ -109,6 +111,17 @@ int sd_ecapa_forward_feats(SdEcapaPlan* plan, const float* feats_dev, int B, int
  * (6144 = mean|std), "asp.uttbias" (128), "pooled" (6144)}.  *C_out receives C. */
 int sd_ecapa_debug_fetch(SdEcapaPlan* plan, const char* name, float* out_dev, int* C_out,
                          void* stream);
+
+/* Per-stage device timing of the forward pass: when enabled, CUDA events are recorded on the
+ * caller's stream at every stage boundary of each subsequent sd_ecapa_embed /
+ * sd_ecapa_forward_feats.  sd_ecapa_profile(plan, 0/1) also resets the record.
+ * sd_ecapa_profile_read waits for the last event and returns, for each of
+ * sd_ecapa_num_stages() stages, its name (32 bytes per entry in `names`) and the elapsed
+ * milliseconds SUMMED over the *n_forwards forwards recorded. */
+int sd_ecapa_profile(SdEcapaPlan* plan, int enable);
+int sd_ecapa_num_stages(void);
+int sd_ecapa_profile_read(SdEcapaPlan* plan, int max_stages, char* names, float* total_ms,
+                          int* n_forwards);
 
 /* FLOPs (2 * MACs of the dense contractions actually issued, padding excluded)
  * of one window of T frames — the figure bench.py's roofline uses. */

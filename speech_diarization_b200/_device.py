@@ -2,6 +2,8 @@
 streams and error checking only (PyTorch is plumbing here, not the arithmetic)."""
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 import torch
 
@@ -24,5 +26,7 @@ def require_cuda(device=None) -> torch.device:
 def to_device_f32(x, device: torch.device) -> torch.Tensor:
     """numpy / torch, any float dtype -> contiguous f32 CUDA tensor (H2D copy if needed)."""
     if isinstance(x, np.ndarray):
-        x = torch.from_numpy(np.ascontiguousarray(x))
+        with warnings.catch_warnings():      # read-only views (frame_audio) are only ever read
+            warnings.simplefilter("ignore", UserWarning)
+            x = torch.from_numpy(np.ascontiguousarray(x))
     return x.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()

@@ -23,6 +23,7 @@ SIGNATURES = {
     "sd_version": (c_int, []),
     "sd_status_string": (c_char_p, [c_int]),
     "sd_last_error": (c_char_p, []),
+    "sd_launch_count": (c_long, []),
     "sd_fbank_num_frames": (c_int, [c_int]),
     "sd_fbank_f32": (c_int, [c_void_p, c_long, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sd_ecapa_plan_create": (c_int, [POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_int, c_int, POINTER(c_void_p)]),
@@ -30,6 +31,9 @@ SIGNATURES = {
     "sd_ecapa_embed": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sd_ecapa_forward_feats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sd_ecapa_debug_fetch": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int), c_void_p]),
+    "sd_ecapa_profile": (c_int, [c_void_p, c_int]),
+    "sd_ecapa_num_stages": (c_int, []),
+    "sd_ecapa_profile_read": (c_int, [c_void_p, c_int, c_char_p, POINTER(c_float), POINTER(c_int)]),
     "sd_ecapa_flops_per_window": (c_double, [c_int]),
     "sd_l2norm_f32": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     "sd_affinity_workspace_bytes": (c_size_t, [c_int, c_int]),

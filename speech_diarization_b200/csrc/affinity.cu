@@ -107,6 +107,7 @@ extern "C" int sd_cosine_distance_rowblock(const float* emb_dev, int N, int D, i
   __half* xs = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~uintptr_t(255));
   normalize_split_kernel<<<(N + 7) / 8, 256, 0, st>>>(emb_dev, N, D, xs);
   SD_CUDA_OK(cudaGetLastError());
+  count_launch();
   GemmParams P;
   init_params(P);
   SD_TRY(make_tmap_f16(&P.tmapA, xs, N, 2 * D, 2 * D, BM));
@@ -144,6 +145,7 @@ extern "C" int sd_window_argmax(const float* x_dev, const float* cent_dev, int N
   window_argmax_kernel<<<grid, 256, (size_t)K * D * 4, static_cast<cudaStream_t>(stream)>>>(
       x_dev, cent_dev, N, K, D, best_dev, score_dev);
   SD_CUDA_OK(cudaGetLastError());
+  count_launch();
   return SD_OK;
 }
 
@@ -152,5 +154,6 @@ extern "C" int sd_adjacent_cosine(const float* x_dev, int N, int D, float* sims_
   if (N < 2) return SD_OK;
   adjacent_cosine_kernel<<<(N - 1 + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, N, D, sims_dev);
   SD_CUDA_OK(cudaGetLastError());
+  count_launch();
   return SD_OK;
 }

@@ -307,5 +307,6 @@ extern "C" int sd_ahc_average_f32(const float* dist_dev, int N, double threshold
   SD_CUDA_OK(cudaLaunchCooperativeKernel((void*)ahc_rounds_kernel, dim3(sms * occ), dim3(AHC_THREADS), args, 0, st));
   ahc_labels_kernel<<<1, 1024, 0, st>>>(S, labels_dev, n_clusters_dev, scratch);
   SD_CUDA_OK(cudaGetLastError());
+  count_launch(4);
   return SD_OK;
 }

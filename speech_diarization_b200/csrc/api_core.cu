@@ -20,6 +20,8 @@ extern "C" const char* sd_status_string(int s) {
 
 extern "C" const char* sd_last_error(void) { return err_buf(); }
 
+extern "C" long sd_launch_count(void) { return launch_counter().load(); }
+
 extern "C" int sd_debug_gemm_f16(const void* A, int M, int K, const void* B, int N, int taps,
                                  int dil, int n_tile, float* D, void* stream) {
   if (!A || !B || !D || M < 1 || N < 1 || K < 64 || K % 64 || taps < 1 || (taps & 1) == 0 ||

@@ -81,6 +81,11 @@ struct SdEcapaPlan {
   float *uttbias = nullptr, *pooled = nullptr;
   std::map<std::pair<int, int>, Program> programs;
   Program* last = nullptr;
+  // optional per-stage timing (CUDA events on the caller's stream; bench.py's roofline leg)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  int forwards_profiled = 0;
 };
 
 namespace {
@@ -277,16 +282,39 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   return SD_OK;
 }
 
+// Stage boundaries recorded when profiling is on (one event BEFORE each stage + one at the end).
+const char* const kStageNames[] = {"fbank", "block0",
+                                   "b1.tdnn1", "b1.res2net", "b1.tdnn2", "b1.se",
+                                   "b2.tdnn1", "b2.res2net", "b2.tdnn2", "b2.se",
+                                   "b3.tdnn1", "b3.res2net", "b3.tdnn2", "b3.se",
+                                   "mfa", "asp.context", "asp.attn", "asp.pool", "fc"};
+constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
+
+void mark(SdEcapaPlan* p, cudaStream_t st) {
+  if (!p->profile) return;
+  if (p->ev_used == p->ev_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { p->profile = false; return; }
+    p->ev_pool.push_back(e);
+  }
+  cudaEventRecord(p->ev_pool[p->ev_used++], st);
+}
+
 int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStream_t st) {
   const int B = pr.B, T = pr.T, Tp = pr.Tp;
   const long R = pr.rows;
+  mark(p, st);  // end of fbank / start of block0
   SD_TRY(launch_gemm<EPI_TDNN>(pr.block0, st));
   for (int b = 0; b < 3; ++b) {
     const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
     const int ld_in = b == 0 ? C1 : C3;
+    mark(p, st);
     SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn1[b], st));
+    mark(p, st);
     for (int i = 0; i < 7; ++i) SD_TRY(launch_gemm<EPI_TDNN>(pr.res[b][i], st));
+    mark(p, st);
     SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn2[b], st));
+    mark(p, st);
     time_mean_kernel<<<dim3(C1 / 256, B), 128, 0, st>>>(p->w, C1, Tp, T, HALO, C1, p->se_mean);
     se_mlp_kernel<<<B, 256, (C1 + SE) * sizeof(float), st>>>(p->se_mean, p->blk[b].se_w1, p->blk[b].se_b1,
                                                              p->blk[b].se_w2t, p->blk[b].se_b2, C1, SE,
@@ -296,14 +324,21 @@ int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStr
     se_apply_kernel<<<grid, 256, 0, st>>>(p->w, C1, p->se_scale, in, ld_in, p->cat + (size_t)b * C1, C3, R,
                                           Tp, C1);
     SD_CUDA_OK(cudaGetLastError());
+    count_launch(3);
   }
+  mark(p, st);
   SD_TRY(launch_gemm<EPI_TDNN>(pr.mfa, st));
+  mark(p, st);
   time_mean_std_kernel<<<dim3(C3 / 256, B), 128, 0, st>>>(p->h, C3, Tp, T, HALO, C3, p->stats);
   // context bias: conv bias + W_mean . mean + W_std . std  (the 2/3 of asp.tdnn that is constant over time)
   dense_rows_kernel<<<(B + 3) / 4, 256, 0, st>>>(p->Wams, p->watt.bias, p->stats, B, 2 * C3, ATT, p->uttbias);
   SD_CUDA_OK(cudaGetLastError());
+  count_launch(2);
+  mark(p, st);
   SD_TRY(launch_gemm<EPI_TDNN>(pr.att, st));
+  mark(p, st);
   SD_TRY(launch_gemm<EPI_POOL>(pr.pool, st));
+  mark(p, st);
   if (l2_normalize) {
     dense_rows_kernel<<<(B + 3) / 4, 256, 0, st>>>(p->Wfc, p->bfc, p->pooled, B, 2 * C3, EMB, p->se_mean);
     l2norm_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->se_mean, B, EMB, 1e-8f, emb);
@@ -311,6 +346,9 @@ int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStr
     dense_rows_kernel<<<(B + 3) / 4, 256, 0, st>>>(p->Wfc, p->bfc, p->pooled, B, 2 * C3, EMB, emb);
   }
   SD_CUDA_OK(cudaGetLastError());
+  count_launch(l2_normalize ? 2 : 1);
+  mark(p, st);  // end of fc
+  if (p->profile) ++p->forwards_profiled;
   p->last = &pr;
   return SD_OK;
 }
@@ -438,6 +476,7 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
 extern "C" int sd_ecapa_plan_destroy(SdEcapaPlan* p) {
   if (!p) return SD_OK;
   cudaDeviceSynchronize();
+  for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   for (void* d : p->allocs) cudaFree(d);
   delete p;
   return SD_OK;
@@ -452,6 +491,7 @@ extern "C" int sd_ecapa_embed(SdEcapaPlan* p, const float* wav_dev, long wav_str
   Program* pr = nullptr;
   SD_TRY(build_program(p, B, T, &pr));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mark(p, st);  // start of fbank
   SD_TRY(fbank_launch(wav_dev, wav_stride, B, n_samples, SD_FBANK_SPEECHBRAIN, 1, p->raw, nullptr,
                       p->feats, pr->Tp, HALO, st));
   return run_trunk(p, *pr, l2_normalize, emb_dev, st);
@@ -464,6 +504,7 @@ extern "C" int sd_ecapa_forward_feats(SdEcapaPlan* p, const float* feats_dev, in
   Program* pr = nullptr;
   SD_TRY(build_program(p, B, T, &pr));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mark(p, st);  // start of the feature repack (reported under "fbank")
   SD_TRY(feats_to_padded_f16(feats_dev, B, T, p->feats, pr->Tp, HALO, st));
   return run_trunk(p, *pr, l2_normalize, emb_dev, st);
 }
@@ -491,6 +532,7 @@ extern "C" int sd_ecapa_debug_fetch(SdEcapaPlan* p, const char* name, float* out
     fetch_interior_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(
         src, ld, off, pr.Tp, pr.T, HALO, C, total, out_dev);
     SD_CUDA_OK(cudaGetLastError());
+    count_launch();
     if (C_out) *C_out = C;
     return SD_OK;
   }
@@ -518,5 +560,38 @@ extern "C" int sd_l2norm_f32(const float* x_dev, int N, int D, float eps, float*
   if (N == 0) return SD_OK;
   l2norm_rows_kernel<<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, N, D, eps, out_dev);
   SD_CUDA_OK(cudaGetLastError());
+  count_launch();
   return SD_OK;
 }
+
+extern "C" int sd_ecapa_profile(SdEcapaPlan* p, int enable) {
+  if (!p) return fail(SD_ERR_ARG, "sd_ecapa_profile: NULL plan");
+  p->profile = enable != 0;
+  p->ev_used = 0;
+  p->forwards_profiled = 0;
+  return SD_OK;
+}
+
+extern "C" int sd_ecapa_profile_read(SdEcapaPlan* p, int max_stages, char* names, float* total_ms,
+                                     int* n_forwards) {
+  if (!p || !names || !total_ms || !n_forwards || max_stages < kNumStages)
+    return fail(SD_ERR_ARG, "sd_ecapa_profile_read: need room for %d stages", kNumStages);
+  const int per = kNumStages + 1;  // events per forward
+  const int nf = p->forwards_profiled;
+  if ((size_t)nf * per != p->ev_used) return fail(SD_ERR_ARG, "profile events out of step (%zu events, %d forwards)", p->ev_used, nf);
+  for (int s = 0; s < kNumStages; ++s) {
+    total_ms[s] = 0.f;
+    snprintf(names + 32 * s, 32, "%s", kStageNames[s]);
+  }
+  if (nf > 0) SD_CUDA_OK(cudaEventSynchronize(p->ev_pool[p->ev_used - 1]));
+  for (int f = 0; f < nf; ++f)
+    for (int s = 0; s < kNumStages; ++s) {
+      float ms = 0.f;
+      SD_CUDA_OK(cudaEventElapsedTime(&ms, p->ev_pool[(size_t)f * per + s], p->ev_pool[(size_t)f * per + s + 1]));
+      total_ms[s] += ms;
+    }
+  *n_forwards = nf;
+  return kNumStages == 0 ? SD_OK : SD_OK;
+}
+
+extern "C" int sd_ecapa_num_stages(void) { return kNumStages; }

@@ -377,6 +377,7 @@ int fbank_launch(const float* wav, long wav_stride, int B, int n_samples, int va
   SD_CUDA_OK(cudaGetLastError());
   fbank_norm_kernel<<<B, 256, 0, stream>>>(raw, T, variant == 1, mean_norm, out_f32, out_f16, Tp, H);
   SD_CUDA_OK(cudaGetLastError());
+  count_launch(2);
   return SD_OK;
 }
 
@@ -384,6 +385,7 @@ int feats_to_padded_f16(const float* feats, int B, int T, __half* out_f16, int T
                         cudaStream_t stream) {
   fbank_norm_kernel<<<B, 256, 0, stream>>>(const_cast<float*>(feats), T, 0, 0, nullptr, out_f16, Tp, H);
   SD_CUDA_OK(cudaGetLastError());
+  count_launch();
   return SD_OK;
 }
 

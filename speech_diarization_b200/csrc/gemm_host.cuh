@@ -73,6 +73,7 @@ inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
   if (tiles <= 0) return SD_OK;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_tc_kernel<EPI, MAX_BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(P);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? SD_OK : SD_ERR_CUDA;
 }
 

@@ -4,8 +4,16 @@
 #include "../../include/sd_b200.h"
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 
 namespace sd {
+// kernels launched by this library since load (bench.py reports it as gpu_launches)
+inline std::atomic<long>& launch_counter() {
+  static std::atomic<long> c{0};
+  return c;
+}
+inline void count_launch(int n = 1) { launch_counter().fetch_add(n, std::memory_order_relaxed); }
+
 inline char* err_buf() {
   static thread_local char buf[512] = {0};
   return buf;

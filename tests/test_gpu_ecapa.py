@@ -1,0 +1,115 @@
+"""ECAPA-TDNN trunk + end-to-end embedding parity against the CPU fp32 oracle on identical
+synthetic audio and identical random-init weights.
+
+Gate (BASELINE.json north_star): cosine similarity of embeddings >= 1 - 1e-4.
+Layer-wise bound: relative L2 error <= 5e-3 (f16 operands / f16 activations, f32 accumulation;
+measured 4e-4 after block0 growing to 1.4e-3 after the MFA layer)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import synth_wave
+from oracle import ecapa_oracle as eo
+from speech_diarization_b200 import _lib, speech_encode as se
+
+pytestmark = pytest.mark.gpu
+COS_TOL = 1e-4
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("B,T", [(3, 151), (5, 101), (2, 26), (1, 10), (7, 248)])
+def test_trunk_layerwise_and_embedding_parity(oracle_model, encoder, B, T):
+    x = eo.synth_features(B, T, seed=B * 100 + T)
+    taps = {}
+    with torch.inference_mode():
+        ref = oracle_model(x, taps).squeeze(1)
+    got = encoder.forward_feats(x).cpu()
+    for name in ("block0", "b1.out", "b2.out", "b3.out", "mfa"):
+        assert _rel(encoder.debug_fetch(name, B, T), taps[name].transpose(1, 2)) < 5e-3, name
+    assert _rel(encoder.debug_fetch("pooled", B, T), taps["pooled"]) < 5e-3
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=1)
+    assert float((1 - cos).max()) < COS_TOL
+    assert _rel(got, ref) < 5e-3
+
+
+@pytest.mark.parametrize("n", [24000, 16000, 4000, 8123])
+def test_encode_batch_matches_oracle(oracle_model, encoder, n):
+    w = synth_wave(6, n, n)
+    w[2, n // 2:] = 0.0           # zero-padded member of a variable-length batch
+    with torch.inference_mode():
+        ref = eo.encode_batch(oracle_model, torch.from_numpy(w)).squeeze(1)
+    out = encoder.encode_batch(torch.from_numpy(w))
+    assert out.shape == (6, 1, 192) and out.dtype == torch.float32 and out.is_cuda
+    cos = torch.nn.functional.cosine_similarity(out.squeeze(1).cpu(), ref, dim=1)
+    assert float((1 - cos).max()) < COS_TOL
+
+
+def test_reference_callables(oracle_model):
+    """ecapa_encode_batch / using_ecapa_encoder / ECAPAEncoder keep the reference's contracts
+    (speech_encode.py:64-78, ecapa_annote.py:6-22)."""
+    from speech_diarization_b200 import ecapa_annote, vad
+    se.register_ecapa_state_dict(oracle_model.state_dict())
+    try:
+        enc = se.using_ecapa_encoder()
+        assert enc is se.using_ecapa_encoder()                      # lru_cache singleton
+        y = synth_wave(1, 16000 * 6, 3)[0]
+        frames = vad.frame_audio(y, 16000, 1500.0, 750.0)           # strided view: uploaded once
+        e_view = se.ecapa_encode_batch(frames)
+        e_copy = se.ecapa_encode_batch(np.ascontiguousarray(frames))
+        assert e_view.shape == (frames.shape[0], 192) and e_view.dtype == np.float32
+        np.testing.assert_array_equal(e_view, e_copy)
+        with torch.inference_mode():
+            ref = eo.encode_batch(oracle_model, torch.from_numpy(np.ascontiguousarray(frames))).squeeze(1)
+        cos = torch.nn.functional.cosine_similarity(torch.from_numpy(e_view), ref, dim=1)
+        assert float((1 - cos).max()) < COS_TOL
+        # float64 input is cast like the reference's .float() (speech_encode.py:76)
+        e64 = se.ecapa_encode_batch(np.ascontiguousarray(frames).astype(np.float64))
+        np.testing.assert_array_equal(e64, e_copy)
+        m = ecapa_annote.ECAPAEncoder(device="cuda")
+        assert m.dimension == 192
+        out = m(torch.from_numpy(np.ascontiguousarray(frames[:3])).cuda())
+        assert out.shape == (3, 192) and out.is_cuda
+        np.testing.assert_allclose(out.cpu().numpy(), e_copy[:3], rtol=0, atol=0)
+    finally:
+        se.register_ecapa_state_dict(None)
+
+
+def test_no_weights_is_an_error(monkeypatch):
+    monkeypatch.delenv("SD_ECAPA_CKPT", raising=False)
+    se.register_ecapa_state_dict(None)
+    with pytest.raises(_lib.SdError):
+        se.using_ecapa_encoder()
+
+
+def test_missing_tensor_is_reported(oracle_model):
+    sd = dict(oracle_model.state_dict())
+    del sd["mfa.conv.conv.weight"]
+    with pytest.raises(_lib.SdError, match="mfa.conv.conv.weight"):
+        se.EcapaEncoderB200(sd, device="cuda:0", max_batch=1, max_samples=4000)
+
+
+def test_batch_properties_full_size(oracle_model, encoder):
+    """BASELINE batch: determinism, batch-composition independence and chunking across the
+    plan's capacity (512 windows through a 64-window plan)."""
+    w = torch.from_numpy(synth_wave(16, 24000, 11)).cuda().repeat(32, 1)       # 512 windows
+    e1 = encoder.embed_device(w, 24000, 512, 24000)
+    e2 = encoder.embed_device(w, 24000, 512, 24000)
+    assert torch.equal(e1, e2)
+    assert torch.equal(e1[:16], e1[16:32])                  # same window, different batch slot
+    single = encoder.embed_device(w[3:4].contiguous(), 24000, 1, 24000)
+    assert torch.equal(single[0], e1[3])
+    n = encoder.embed_device(w, 24000, 512, 24000, l2_normalize=True)
+    assert torch.allclose(n.norm(dim=1), torch.ones(512, device="cuda"), atol=1e-5)
+    assert float((n - e1 / (e1.norm(dim=1, keepdim=True) + 1e-8)).abs().max()) < 1e-6
+
+
+def test_unsupported_and_bad_arguments(encoder):
+    with pytest.raises(_lib.SdError):
+        encoder.encode_batch(torch.zeros(2, 24000), wav_lens=torch.tensor([1.0, 0.5]))
+    with pytest.raises(ValueError):
+        encoder.embed_device(torch.zeros(100, device="cuda"), 100, 1, 100)
+    assert encoder.embed_device(torch.zeros(0, device="cuda"), 1, 0, 24000).shape == (0, 192)
