@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 diarization hot path.
+
+Metric (BASELINE.json): ECAPA embeddings/sec on 1.5 s windows (0.75 s hop, batch 512, 1 h of
+synthetic 16 kHz multi-speaker audio per GPU), plus AHC milliseconds at N = 20 000 segments.
+
+A "step" = one pass of the hot path over one batch: 512 windows addressed in place in the
+HBM-resident audio -> fused fbank -> ECAPA-TDNN (C = 1024) -> 192-d L2-normalised embeddings
+(for N > 1 GPUs followed by the NCCL all-gather of the step's embeddings, BASELINE config 3).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 16000
+WIN = 24000          # 1.5 s
+HOP = 12000          # 0.75 s
+BATCH = 512
+AUDIO_SECONDS = 3600
+METRIC = "ECAPA embeddings/sec (1.5s windows)"
+WORKLOAD = ("configs[1]: ECAPA-TDNN C=1024 embedding of 1 h synthetic 16 kHz audio, 1.5 s windows / 0.75 s hop, "
+            "batch 512 per step")
+
+
+# ------------------------------------------------------------------------------ synthetic audio
+def synth_audio(seconds: int, n_speakers: int, seed: int, device) -> torch.Tensor:
+    """Multi-speaker synthetic speech-like audio: alternating 2-6 s turns, each speaker a
+    harmonic stack at its own f0 with a 3-formant envelope, white noise at -30 dB, 0.3 s silences."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    n = seconds * SR
+    t = torch.arange(n, device=device, dtype=torch.float32) / SR
+    out = torch.zeros(n, device=device)
+    # turn boundaries on the host
+    pos, turns = 0, []
+    while pos < n:
+        dur = int((2.0 + 4.0 * torch.rand(1, generator=g).item()) * SR)
+        spk = int(torch.randint(0, n_speakers, (1,), generator=g).item())
+        turns.append((pos, min(n, pos + dur), spk))
+        pos += dur + int(0.3 * SR)
+    spk_of = torch.full((n,), -1, dtype=torch.int64)
+    for a, b, s in turns:
+        spk_of[a:b] = s
+    spk_of = spk_of.to(device)
+    for k in range(n_speakers):
+        f0 = 110.0 * (1.0 + 0.5 * k)
+        formants = [500.0 + 120.0 * k, 1500.0 + 150.0 * k, 2500.0 + 100.0 * k]
+        sig = torch.zeros(n, device=device)
+        for h in range(1, 25):
+            f = f0 * h
+            if f > 7600:
+                break
+            amp = sum(1.0 / (1.0 + ((f - fc) / 150.0) ** 2) for fc in formants) + 0.05
+            sig += amp * torch.sin(2 * np.pi * f * t + 0.7 * h * (k + 1))
+        sig = 0.1 * sig / sig.abs().max()
+        out += torch.where(spk_of == k, sig, torch.zeros_like(sig))
+    noise = torch.randn(n, generator=torch.Generator(device=device).manual_seed(seed + 1), device=device)
+    out += 10 ** (-30 / 20) * 0.1 * noise
+    return out.clamp_(-1.0, 1.0)
+
+
+# ---------------------------------------------------------------------------- clocks sampling
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines: list[str] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_setup(state_dict):
+    from oracle import ecapa_oracle          # the ONLY place bench.py touches oracle/: the CPU baseline legs
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = ecapa_oracle.ECAPA_TDNN().eval()
+    model.load_state_dict(state_dict)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return ecapa_oracle, model
+
+
+def cpu_baseline(state_dict, audio_host: np.ndarray, n_windows: int = 64) -> dict:
+    """The oracle (CPU fp32 port of the reference path) on a bounded sample of the same workload."""
+    eo, model = cpu_reference_setup(state_dict)
+    idx = np.arange(WIN)[None, :] + HOP * np.arange(n_windows)[:, None]
+    wav = torch.from_numpy(audio_host[idx])
+    with torch.inference_mode():
+        eo.encode_batch(model, wav[:8])                      # warm-up
+        t0 = time.perf_counter()
+        done = 0
+        while True:
+            for b0 in range(0, n_windows, 32):               # reference batch size 32 (anti_stick_diarize.py:134)
+                eo.encode_batch(model, wav[b0:b0 + 32])
+            done += n_windows
+            dt = time.perf_counter() - t0
+            if dt > 10.0 or done >= 8 * n_windows:
+                break
+    return {"value": done / dt, "unit": "embeddings/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} windows of 1.5 s from the same audio, batches of 32, oracle/ecapa_oracle.py "
+                      f"(CPU fp32 PyTorch port of speechbrain fbank + ECAPA-TDNN), {dt:.1f} s"}
+
+
+def run_reference_arm(args, rank: int) -> None:
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference's own
+    speechbrain dependency is not installable here), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from speech_diarization_b200.weights import random_ecapa_state_dict
+    sd = random_ecapa_state_dict(0)
+    eo, model = cpu_reference_setup(sd)
+    per_step = 32
+    audio = synth_audio(120, 4, 0, "cpu").numpy()
+    idx = np.arange(WIN)[None, :] + HOP * np.arange(per_step)[:, None]
+    wav = torch.from_numpy(audio[idx])
+    with torch.inference_mode():
+        for _ in range(max(1, min(args.warmup, 2))):
+            eo.encode_batch(model, wav)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eo.encode_batch(model, wav)
+        dt = time.perf_counter() - t0
+    val = per_step * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "embeddings/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "window_s": 1.5, "hop_s": 0.75,
+                       "sample": f"{per_step} windows per step (bounded sample of the 512-window batch)"},
+            "cpu_baseline": {"value": val, "unit": "embeddings/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{per_step} windows x {args.steps} steps, oracle/ecapa_oracle.py"},
+            "e2e": {"value": val, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- AHC leg
+def same_partition(a, b) -> bool:
+    fwd, bwd = {}, {}
+    for x, y in zip(a.tolist(), b.tolist()):
+        if fwd.setdefault(x, y) != y or bwd.setdefault(y, x) != x:
+            return False
+    return True
+
+
+def ahc_leg(device, with_cpu: bool) -> dict:
+    """BASELINE config 4: cosine affinity + AHC at N = 20 000 (K = 8, sigma = 0.02, cos_thr = 0.68)."""
+    from speech_diarization_b200 import clustering
+    out = {}
+    for N in (5000, 20000):
+        rng = np.random.default_rng(0)
+        c = rng.standard_normal((8, 192)); c /= np.linalg.norm(c, axis=1, keepdims=True)
+        lab = rng.integers(0, 8, N)
+        X = (c[lab] + 0.02 * rng.standard_normal((N, 192))).astype(np.float32)
+        xd = torch.from_numpy(X).to(device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        best_aff, best_ahc = 1e9, 1e9
+        for rep in range(4):
+            ev[0].record()
+            dist = clustering.cosine_distance_device(xd)
+            ev[1].record()
+            labels, ncl = clustering.ahc_average_device(dist, 1 - 0.68)
+            ev[2].record()
+            torch.cuda.synchronize()
+            if rep:                              # rep 0 = warm-up
+                best_aff = min(best_aff, ev[0].elapsed_time(ev[1]))
+                best_ahc = min(best_ahc, ev[1].elapsed_time(ev[2]))
+        ok = same_partition(labels.cpu().numpy(), lab)
+        out[f"n{N}"] = {"affinity_ms": best_aff, "ahc_ms": best_ahc, "clusters": int(ncl.item()),
+                        "labels_match_planted": bool(ok),
+                        "ahc_frac_of_hbm_roofline": ((4.0 * N * N + 12.0 * N * (N - 8)) / (best_ahc * 1e-3)) / 1e9 / PEAK_HBM}
+        if with_cpu and N == 5000:
+            from oracle import cluster_oracle
+            t0 = time.perf_counter()
+            ref = cluster_oracle.cluster_embeddings(X, "agglo", 0.68)
+            out[f"n{N}"]["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+            out[f"n{N}"]["labels_match_cpu"] = bool(same_partition(labels.cpu().numpy(), ref))
+        del dist, labels
+        torch.cuda.empty_cache()
+    out["cpu_note"] = "cpu_ms = sklearn cosine_similarity + AgglomerativeClustering (diar_diag.py:219-226) at N=5000; " \
+                      "the same call at N=20000 takes ~35 s on 8 cores (BASELINE.md §2) and is not repeated here"
+    return out
+
+
+PEAK_HBM = 6450.9
+PEAK_TF = 1430.4
+
+
+def load_peaks():
+    global PEAK_HBM, PEAK_TF
+    src = "fallback 6650 GB/s, 1590 TFLOP/s (B200_PROFILING.md)"
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        PEAK_HBM = float(pk["hbm_gbs"]); PEAK_TF = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
+        src = "MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained)"
+    except Exception:
+        PEAK_HBM, PEAK_TF = 6650.0, 1590.0
+    return src
+
+
+# ----------------------------------------------------------------------------------- main arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ahc", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+    from speech_diarization_b200 import _lib, speech_encode, vad
+    from speech_diarization_b200.weights import random_ecapa_state_dict
+
+    peaks_src = load_peaks()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+
+    # ---- workload: 1 h of audio per rank (weak scaling), resident in HBM; 512-window batches
+    audio = synth_audio(AUDIO_SECONDS, 4, seed=rank, device=device)
+    n_windows = 1 + (audio.numel() - WIN) // HOP                    # 4799 (vad.frame_audio semantics)
+    n_batches = n_windows // BATCH                                  # 9 full batches, cycled
+    sd = random_ecapa_state_dict(0)
+    enc = speech_encode.EcapaEncoderB200(sd, device=device, max_batch=BATCH, max_samples=WIN)
+    emb = torch.empty((BATCH, 192), dtype=torch.float32, device=device)
+    gathered = torch.empty((world * BATCH, 192), dtype=torch.float32, device=device) if world > 1 else None
+
+    def step(i: int) -> None:
+        off = (i % n_batches) * BATCH * HOP
+        enc.embed_device(audio[off:], HOP, BATCH, WIN, l2_normalize=True, out=emb)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, emb)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs ("value") with per-stage CUDA events
+    enc.profile(True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = lib.sd_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.sd_launch_count() - launches0
+    clk = clocks.stop()
+    stage_ms, n_fwd = enc.profile_read()
+    enc.profile(False)
+    t = torch.tensor([ms_total], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # ---- timed region 2: end to end through the public API with HOST buffers (pinned)
+    host_audio = torch.empty(audio.shape, dtype=torch.float32, pin_memory=True)
+    host_audio.copy_(audio)
+    torch.cuda.synchronize()
+    frames = vad.frame_audio(host_audio.numpy(), SR, 1500.0, 750.0)         # strided view, no copy
+    speech_encode.register_ecapa_state_dict(sd)          # what a user does once; using_ecapa_encoder() builds its plan
+    for i in range(2):
+        speech_encode.ecapa_encode_batch(frames[i * BATCH:(i + 1) * BATCH])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        b = (args.warmup + i) % n_batches
+        out_host = speech_encode.ecapa_encode_batch(frames[b * BATCH:(b + 1) * BATCH])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * BATCH * args.steps / e2e_s
+    h2d = ((BATCH - 1) * HOP + WIN) * 4
+    d2h = BATCH * 192 * 4
+    assert out_host.shape == (BATCH, 192)
+
+    if rank == 0:
+        T = lib.sd_fbank_num_frames(WIN)
+        mfa_flops = 2.0 * 3072 * 3072 * T * BATCH                  # algorithmic FLOPs of one MFA GEMM launch
+        mfa_ms = stage_ms["mfa"] / max(n_fwd, 1)
+        achieved = mfa_flops / (mfa_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["mfa_dram_bytes_per_launch"]
+        except Exception:
+            pass
+        step_flops = lib.sd_ecapa_flops_per_window(T) * BATCH
+        per_stage = {k: round(v / max(n_fwd, 1), 4) for k, v in stage_ms.items()}
+        line = {
+            "metric": METRIC, "value": value, "unit": "embeddings/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "window_s": 1.5, "hop_s": 0.75, "batch": BATCH, "frames_per_window": T,
+                       "audio_seconds_per_gpu": AUDIO_SECONDS, "windows_per_gpu": int(n_windows),
+                       "weights": "synthetic random-init, speechbrain ECAPA-TDNN C=1024 shapes (20.77 M params)",
+                       "arithmetic": "f16 operands, f32 accumulation (tcgen05 kind::f16); fbank / SE / pooling stats f32",
+                       "l2_cold": "inputs larger than L2: each step reads a different 24.6 MB slice of the 230 MB "
+                                  "resident audio and streams ~1.7 GB of activations (L2 = 126 MB)",
+                       "collective": "all_gather of the step's [512,192] embeddings (NCCL)" if world > 1 else "none",
+                       "peaks": peaks_src},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "embeddings/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "speech_encode.ecapa_encode_batch(vad.frame_audio(pinned host audio)[512 windows])"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<EPI_TDNN,256> — MFA 1x1 conv 3072->3072 "
+                                                      "(50% of the trunk's FLOPs)",
+                         "achieved": achieved, "peak": PEAK_TF, "unit": "TFLOP/s", "frac": achieved / PEAK_TF,
+                         "traffic": traffic, "algorithmic_flops_per_launch": mfa_flops, "launch_ms": mfa_ms,
+                         "whole_step": {"tflops": step_flops / (ms_total / args.steps * 1e-3) / 1e12,
+                                        "frac": step_flops / (ms_total / args.steps * 1e-3) / 1e12 / PEAK_TF,
+                                        "flops_per_step": step_flops},
+                         "stage_ms": per_stage},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sd, host_audio.numpy())
+        else:
+            line["cpu_baseline"] = None
+        if world == 1 and not args.no_ahc:
+            line["ahc"] = ahc_leg(device, with_cpu=not args.no_cpu_baseline)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -162,6 +162,22 @@ class EcapaEncoderB200:
                                                         out.data_ptr(), _lib.stream_ptr()), "sd_ecapa_forward_feats")
         return out
 
+    def profile(self, enable: bool) -> None:
+        """Record CUDA events at every stage boundary of subsequent forwards (and reset the record)."""
+        _lib.check(self._lib.sd_ecapa_profile(self._plan, int(bool(enable))), "sd_ecapa_profile")
+
+    def profile_read(self) -> tuple[dict, int]:
+        """({stage: total milliseconds over the recorded forwards}, number of forwards)."""
+        ns = self._lib.sd_ecapa_num_stages()
+        names = ctypes.create_string_buffer(32 * ns)
+        ms = (ctypes.c_float * ns)()
+        nf = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sd_ecapa_profile_read(self._plan, ns, names, ms, ctypes.byref(nf)),
+                       "sd_ecapa_profile_read")
+        out = {names.raw[32 * i:32 * (i + 1)].split(b"\0")[0].decode(): float(ms[i]) for i in range(ns)}
+        return out, nf.value
+
     def debug_fetch(self, name: str, B: int, T: int) -> torch.Tensor:
         big = torch.empty((B * T * 3072,), dtype=torch.float32, device=self.device)
         C = ctypes.c_int(0)
