@@ -58,7 +58,7 @@ struct BlockW {
 struct Program {     // launch parameters for one (B, T) shape
   int B = 0, T = 0, Tp = 0;
   long rows = 0;
-  GemmParams block0, tdnn1[3], res[3][7], tdnn2[3], mfa, att, pool;
+  GemmParams block0, tdnn1[3], res[3][7], tdnn2[3], mfa, ctx, att, pool, fc;
 };
 
 }  // namespace
@@ -71,14 +71,16 @@ struct SdEcapaPlan {
   TdnnW w0;
   BlockW blk[3];
   TdnnW wmfa, watt;
-  float* Wams = nullptr;  // asp.tdnn weight, mean|std columns [ATT, 2*C3] f32
+  __half* Wams = nullptr; // asp.tdnn weight, mean|std columns [ATT, 2*C3] f16
   __half* Wa2 = nullptr;  // asp.conv weight [C3, ATT] f16
-  float *Wfc = nullptr, *bfc = nullptr;  // fc with asp_bn folded in, [EMB, 2*C3]
+  __half* Wfc = nullptr;  // fc with asp_bn folded in, [EMB, 2*C3] f16
+  float* bfc = nullptr;
   // activations
   __half *feats = nullptr, *x0 = nullptr, *cat = nullptr, *u = nullptr, *v = nullptr, *w = nullptr;
   __half *s[2] = {nullptr, nullptr}, *h = nullptr, *attn = nullptr;
   float *raw = nullptr, *se_mean = nullptr, *se_scale = nullptr, *stats = nullptr;
-  float *uttbias = nullptr, *pooled = nullptr;
+  float *uttbias = nullptr, *pooled = nullptr, *emb_tmp = nullptr;
+  __half *stats_h = nullptr, *pooled_h = nullptr;
   std::map<std::pair<int, int>, Program> programs;
   Program* last = nullptr;
   // optional per-stage timing (CUDA events on the caller's stream; bench.py's roofline leg)
@@ -210,14 +212,14 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   const long R = pr.rows;
   // block0: k = 5 over the 128-padded mel channels
   SD_TRY(setup_tdnn_gemm(pr.block0, p->feats, R, FEAT_P, FEAT_P, p->w0, C1, 5 * FEAT_P, 256, FEAT_P,
-                         5, 1, 0, pr, p->x0, C1, 0, EF_RELU_BN | EF_REFLECT));
+                         5, 1, 0, pr, p->x0, C1, 0, EF_REFLECT));
   for (int b = 0; b < 3; ++b) {
     const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
     const int ld_in = b == 0 ? C1 : C3;
     const BlockW& bw = p->blk[b];
     // tdnn1: 1x1, also copies sub-band 0 into v (Res2Net passes it through)
     SD_TRY(setup_tdnn_gemm(pr.tdnn1[b], in, R, C1, ld_in, bw.tdnn1, C1, C1, 256, C1, 1, 1, 0, pr,
-                           p->u, C1, 0, EF_RELU_BN));
+                           p->u, C1, 0, 0));
     pr.tdnn1[b].epi.out2 = p->v;
     pr.tdnn1[b].epi.ld_out2 = C1;
     pr.tdnn1[b].epi.out2_cols = SUB;
@@ -228,7 +230,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
       const int a_col0 = i == 1 ? SUB : 0;
       GemmParams& G = pr.res[b][i - 1];
       SD_TRY(setup_tdnn_gemm(G, A, R, a_cols, a_cols, bw.res[i - 1], SUB, 3 * SUB, 128, SUB, 3,
-                             bw.dil, a_col0, pr, p->v, C1, i * SUB, EF_RELU_BN | EF_REFLECT));
+                             bw.dil, a_col0, pr, p->v, C1, i * SUB, EF_REFLECT));
       if (i < 7) {
         G.epi.add_src = p->u;
         G.epi.ld_add = C1;
@@ -238,13 +240,55 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
       }
     }
     SD_TRY(setup_tdnn_gemm(pr.tdnn2[b], p->v, R, C1, C1, bw.tdnn2, C1, C1, 256, C1, 1, 1, 0, pr,
-                           p->w, C1, 0, EF_RELU_BN));
+                           p->w, C1, 0, 0));
   }
   SD_TRY(setup_tdnn_gemm(pr.mfa, p->cat, R, C3, C3, p->wmfa, C3, C3, 256, C3, 1, 1, 0, pr, p->h, C3,
-                         0, EF_RELU_BN));
+                         0, 0));
   SD_TRY(setup_tdnn_gemm(pr.att, p->h, R, C3, C3, p->watt, ATT, C3, 128, C3, 1, 1, 0, pr, p->attn,
-                         ATT, 0, EF_RELU_BN | EF_TANH | EF_UTT_BIAS));
+                         ATT, 0, 0));
   pr.att.epi.utt_bias = p->uttbias;
+  // context bias: uttbias[b, :] = W_{mean|std} . stats[b]   (per-utterance dense layer, M = B rows)
+  {
+    GemmParams& P = pr.ctx;
+    init_params(P);
+    SD_TRY(make_tmap_f16(&P.tmapA, p->stats_h, B, 2 * C3, 2 * C3, BM));
+    SD_TRY(make_tmap_f16(&P.tmapB, p->Wams, ATT, 2 * C3, 2 * C3, ATT));
+    P.num_m_blocks = (B + BM - 1) / BM;
+    P.num_n_blocks = 1;
+    P.n_tile = ATT;
+    P.idesc = make_idesc_f16(ATT, 0);
+    P.num_kiters = 2 * C3 / BK;
+    for (int c = 0; c < P.num_kiters; ++c) {
+      P.kit[c].a_col = c * BK;
+      P.kit[c].b_col = c * BK;
+      P.kit[c].accum = c > 0;
+    }
+    P.epi.M_rows = B;
+    P.epi.N_cols = ATT;
+    P.epi.out = p->uttbias;
+    P.epi.ld_out = ATT;
+  }
+  // final FC (asp_bn folded): emb[b, :] = Wfc . pooled[b] + bfc
+  {
+    GemmParams& P = pr.fc;
+    init_params(P);
+    SD_TRY(make_tmap_f16(&P.tmapA, p->pooled_h, B, 2 * C3, 2 * C3, BM));
+    SD_TRY(make_tmap_f16(&P.tmapB, p->Wfc, EMB, 2 * C3, 2 * C3, EMB));
+    P.num_m_blocks = (B + BM - 1) / BM;
+    P.num_n_blocks = 1;
+    P.n_tile = EMB;
+    P.idesc = make_idesc_f16(EMB, 0);
+    P.num_kiters = 2 * C3 / BK;
+    for (int c = 0; c < P.num_kiters; ++c) {
+      P.kit[c].a_col = c * BK;
+      P.kit[c].b_col = c * BK;
+      P.kit[c].accum = c > 0;
+    }
+    P.epi.M_rows = B;
+    P.epi.N_cols = EMB;
+    P.epi.ld_out = EMB;
+    P.epi.bias = p->bfc;   // out pointer is set per call
+  }
   // pooling GEMM: rows = channels of asp.conv, columns = the Tp rows of one utterance
   {
     GemmParams& P = pr.pool;
@@ -255,6 +299,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
                   "kernel yet (T=%d)", 256 - 2 * HALO, (256 - 2 * HALO) * 0.01, T);
     SD_TRY(make_tmap_f16(&P.tmapA, p->Wa2, C3, ATT, ATT, BM));
     SD_TRY(make_tmap_f16(&P.tmapB, p->attn, R, ATT, ATT, pr.Tp));
+    SD_TRY(make_tmap_f16(&P.tmapH, p->h, R, C3, C3, pr.Tp));
     P.num_m_blocks = C3 / BM;
     P.num_n_blocks = B;
     P.n_tile = pr.Tp;
@@ -275,6 +320,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     P.epi.gmean = p->stats;   // [B, 2*C3]: mean | std
     P.epi.ld_gmean = 2 * C3;
     P.epi.pooled = p->pooled;
+    P.epi.pooled_h = p->pooled_h;
     P.epi.C = C3;
   }
   auto ins = p->programs.emplace(key, pr);
@@ -316,9 +362,8 @@ int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStr
     SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn2[b], st));
     mark(p, st);
     time_mean_kernel<<<dim3(C1 / 256, B), 128, 0, st>>>(p->w, C1, Tp, T, HALO, C1, p->se_mean);
-    se_mlp_kernel<<<B, 256, (C1 + SE) * sizeof(float), st>>>(p->se_mean, p->blk[b].se_w1, p->blk[b].se_b1,
-                                                             p->blk[b].se_w2t, p->blk[b].se_b2, C1, SE,
-                                                             p->se_scale);
+    se_mlp_kernel<<<dim3((B + 3) / 4, C1 / 256), 256, 4 * (C1 + SE) * sizeof(float), st>>>(
+        p->se_mean, p->blk[b].se_w1, p->blk[b].se_b1, p->blk[b].se_w2t, p->blk[b].se_b2, B, C1, SE, p->se_scale);
     const long vecs = R * (C1 / 8);
     const int grid = (int)((vecs + 255) / 256 < 148L * 16 ? (vecs + 255) / 256 : 148L * 16);
     se_apply_kernel<<<grid, 256, 0, st>>>(p->w, C1, p->se_scale, in, ld_in, p->cat + (size_t)b * C1, C3, R,
@@ -329,24 +374,26 @@ int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStr
   mark(p, st);
   SD_TRY(launch_gemm<EPI_TDNN>(pr.mfa, st));
   mark(p, st);
-  time_mean_std_kernel<<<dim3(C3 / 256, B), 128, 0, st>>>(p->h, C3, Tp, T, HALO, C3, p->stats);
-  // context bias: conv bias + W_mean . mean + W_std . std  (the 2/3 of asp.tdnn that is constant over time)
-  dense_rows_kernel<<<(B + 3) / 4, 256, 0, st>>>(p->Wams, p->watt.bias, p->stats, B, 2 * C3, ATT, p->uttbias);
+  time_mean_std_kernel<<<dim3(C3 / 256, B), 128, 0, st>>>(p->h, C3, Tp, T, HALO, C3, p->stats, p->stats_h);
   SD_CUDA_OK(cudaGetLastError());
-  count_launch(2);
+  count_launch(1);
+  // context bias: W_mean . mean + W_std . std  (the 2/3 of asp.tdnn that is constant over time)
+  SD_TRY(launch_gemm<EPI_F32>(pr.ctx, st));
   mark(p, st);
-  SD_TRY(launch_gemm<EPI_TDNN>(pr.att, st));
+  SD_TRY(launch_gemm<EPI_ATT>(pr.att, st));
   mark(p, st);
   SD_TRY(launch_gemm<EPI_POOL>(pr.pool, st));
   mark(p, st);
-  if (l2_normalize) {
-    dense_rows_kernel<<<(B + 3) / 4, 256, 0, st>>>(p->Wfc, p->bfc, p->pooled, B, 2 * C3, EMB, p->se_mean);
-    l2norm_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->se_mean, B, EMB, 1e-8f, emb);
-  } else {
-    dense_rows_kernel<<<(B + 3) / 4, 256, 0, st>>>(p->Wfc, p->bfc, p->pooled, B, 2 * C3, EMB, emb);
+  {
+    GemmParams fc = pr.fc;  // the output pointer varies per call
+    fc.epi.out = l2_normalize ? p->emb_tmp : emb;
+    SD_TRY(launch_gemm<EPI_F32>(fc, st));
+    if (l2_normalize) {
+      l2norm_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->emb_tmp, B, EMB, 1e-8f, emb);
+      SD_CUDA_OK(cudaGetLastError());
+      count_launch(1);
+    }
   }
-  SD_CUDA_OK(cudaGetLastError());
-  count_launch(l2_normalize ? 2 : 1);
   mark(p, st);  // end of fc
   if (p->profile) ++p->forwards_profiled;
   p->last = &pr;
@@ -406,9 +453,10 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
     {
       const float* W;
       SD_TRY(sd.get("asp.tdnn.conv.conv.weight", (int64_t)ATT * 3 * C3, &W));
-      std::vector<float> ms((size_t)ATT * 2 * C3);
+      std::vector<__half> ms((size_t)ATT * 2 * C3);
       for (int o = 0; o < ATT; ++o)
-        for (int c = 0; c < 2 * C3; ++c) ms[(size_t)o * 2 * C3 + c] = W[(size_t)o * 3 * C3 + C3 + c];
+        for (int c = 0; c < 2 * C3; ++c)
+          ms[(size_t)o * 2 * C3 + c] = __float2half_rn(W[(size_t)o * 3 * C3 + C3 + c]);
       SD_TRY(upload(p, &p->Wams, ms));
       const float* W2;
       SD_TRY(sd.get("asp.conv.conv.weight", (int64_t)C3 * ATT, &W2));
@@ -427,13 +475,14 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
       SD_TRY(sd.get("asp_bn.norm.running_var", 2 * C3, &rv));
       SD_TRY(sd.get("fc.conv.weight", (int64_t)EMB * 2 * C3, &W));
       SD_TRY(sd.get("fc.conv.bias", EMB, &b));
-      std::vector<float> wf((size_t)EMB * 2 * C3), bf(EMB);
+      std::vector<__half> wf((size_t)EMB * 2 * C3);
+      std::vector<float> bf(EMB);
       for (int o = 0; o < EMB; ++o) {
         double acc = b[o];
         for (int k = 0; k < 2 * C3; ++k) {
           const double sc = (double)g[k] / sqrt((double)rv[k] + 1e-5);
           const double sh = (double)be[k] - (double)rm[k] * sc;
-          wf[(size_t)o * 2 * C3 + k] = (float)((double)W[(size_t)o * 2 * C3 + k] * sc);
+          wf[(size_t)o * 2 * C3 + k] = __float2half_rn((float)((double)W[(size_t)o * 2 * C3 + k] * sc));
           acc += (double)W[(size_t)o * 2 * C3 + k] * sh;
         }
         bf[o] = (float)acc;
@@ -460,6 +509,9 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
     SD_TRY(dev_alloc(p, (void**)&p->stats, MB * 2 * C3 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->uttbias, MB * ATT * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->pooled, MB * 2 * C3 * 4, true));
+    SD_TRY(dev_alloc(p, (void**)&p->emb_tmp, MB * EMB * 4, true));
+    SD_TRY(dev_alloc(p, (void**)&p->stats_h, MB * 2 * C3 * 2, true));
+    SD_TRY(dev_alloc(p, (void**)&p->pooled_h, MB * 2 * C3 * 2, true));
     SD_CUDA_OK(cudaDeviceSynchronize());
     return SD_OK;
   };

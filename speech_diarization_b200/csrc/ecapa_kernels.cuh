@@ -48,15 +48,19 @@ time_mean_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H, int
 }
 
 // mean and std (uniform weights 1/T, eps 1e-12) over interior frames; stats[b] = [mean(C), std(C)].
+// ONE pass over the activations: sums of (x - k) and (x - k)^2 with k = the channel's first
+// frame, which removes the cancellation of the naive E[x^2] - E[x]^2 form
+// (var = (S2 - S1^2 / T) / T is shift-invariant).
 __global__ void __launch_bounds__(128)
 time_mean_std_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H, int C,
-                     float* __restrict__ stats /*[B, 2C]*/) {
+                     float* __restrict__ stats /*[B, 2C]*/, __half* __restrict__ stats_h /*[B, 2C] or null*/) {
   const int b = blockIdx.y;
   const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
   if (c >= C) return;
   const __half2* p = reinterpret_cast<const __half2*>(x + (static_cast<size_t>(b) * Tp + H) * ld + c);
   const size_t step = static_cast<size_t>(ld) / 2;
-  float s0 = 0.f, s1 = 0.f;
+  const float2 k = __half22float2(p[0]);
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
   int t = 0;
   for (; t + 8 <= T; t += 8) {
     __half2 v[8];
@@ -65,69 +69,87 @@ time_mean_std_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H,
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float2 f = __half22float2(v[j]);
-      s0 += f.x;
-      s1 += f.y;
+      const float d0 = f.x - k.x, d1 = f.y - k.y;
+      s0 += d0;
+      s1 += d1;
+      q0 = fmaf(d0, d0, q0);
+      q1 = fmaf(d1, d1, q1);
     }
   }
   for (; t < T; ++t) {
     const float2 f = __half22float2(p[t * step]);
-    s0 += f.x;
-    s1 += f.y;
+    const float d0 = f.x - k.x, d1 = f.y - k.y;
+    s0 += d0;
+    s1 += d1;
+    q0 = fmaf(d0, d0, q0);
+    q1 = fmaf(d1, d1, q1);
   }
   const float inv = 1.0f / static_cast<float>(T);
-  const float m0 = s0 * inv, m1 = s1 * inv;
-  float q0 = 0.f, q1 = 0.f;
-  t = 0;
-  for (; t + 8 <= T; t += 8) {
-    __half2 v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = p[(t + j) * step];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 f = __half22float2(v[j]);
-      q0 = fmaf(f.x - m0, f.x - m0, q0);
-      q1 = fmaf(f.y - m1, f.y - m1, q1);
-    }
-  }
-  for (; t < T; ++t) {
-    const float2 f = __half22float2(p[t * step]);
-    q0 = fmaf(f.x - m0, f.x - m0, q0);
-    q1 = fmaf(f.y - m1, f.y - m1, q1);
-  }
+  const float m0 = k.x + s0 * inv, m1 = k.y + s1 * inv;
+  const float v0 = (q0 - s0 * s0 * inv) * inv, v1 = (q1 - s1 * s1 * inv) * inv;
   float* o = stats + static_cast<size_t>(b) * 2 * C;
   o[c] = m0;
   o[c + 1] = m1;
-  o[C + c] = sqrtf(fmaxf(q0 * inv, 1e-12f));
-  o[C + c + 1] = sqrtf(fmaxf(q1 * inv, 1e-12f));
+  const float d0 = sqrtf(fmaxf(v0, 1e-12f)), d1 = sqrtf(fmaxf(v1, 1e-12f));
+  o[C + c] = d0;
+  o[C + c + 1] = d1;
+  if (stats_h) {  // f16 copy: A operand of the context-bias GEMM
+    __half* oh = stats_h + static_cast<size_t>(b) * 2 * C;
+    *reinterpret_cast<__half2*>(oh + c) = __floats2half2_rn(m0, m1);
+    *reinterpret_cast<__half2*>(oh + C + c) = __floats2half2_rn(d0, d1);
+  }
 }
 
 // SE excitation: scale[b] = sigmoid(W2 relu(W1 mean[b] + b1) + b2).
-// W1 [S][C] row-major, W2t [S][C] (= conv2 weight transposed).  grid B, block 256.
+// W1 [S][C] row-major, W2t [S][C] (= conv2 weight transposed).  One CTA handles 4 utterances (the
+// weights are read from L2 once per 4) and one 256-channel slice of the output; the cheap hidden
+// layer is recomputed by each of the C/256 slices.  grid (ceil(B/4), C/256), block 256,
+// dynamic smem 4*(C+S) floats.
 __global__ void __launch_bounds__(256)
 se_mlp_kernel(const float* __restrict__ mean, const float* __restrict__ W1,
               const float* __restrict__ b1, const float* __restrict__ W2t,
-              const float* __restrict__ b2, int C, int S, float* __restrict__ scale) {
+              const float* __restrict__ b2, int B, int C, int S, float* __restrict__ scale) {
   extern __shared__ float sm[];
-  float* m = sm;       // [C]
-  float* hid = sm + C; // [S]
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < C; i += 256) m[i] = mean[static_cast<size_t>(b) * C + i];
+  float* m = sm;            // [4][C]
+  float* hid = sm + 4 * C;  // [4][S]
+  const int b0 = blockIdx.x * 4, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = min(4, B - b0);
+  for (int i = tid; i < 4 * C; i += 256) {
+    const int u = i / C;
+    m[i] = u < nb ? mean[static_cast<size_t>(b0 + u) * C + (i - u * C)] : 0.f;
+  }
   __syncthreads();
   for (int j = warp; j < S; j += 8) {
     const float4* w = reinterpret_cast<const float4*>(W1 + static_cast<size_t>(j) * C);
-    float acc = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int i = lane; i < C / 4; i += 32) {
       const float4 wv = __ldg(w + i);
-      acc += wv.x * m[4 * i] + wv.y * m[4 * i + 1] + wv.z * m[4 * i + 2] + wv.w * m[4 * i + 3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 mv = *reinterpret_cast<const float4*>(m + u * C + 4 * i);
+        acc[u] += wv.x * mv.x + wv.y * mv.y + wv.z * mv.z + wv.w * mv.w;
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) hid[j] = fmaxf(acc + b1[j], 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float a = warp_sum(acc[u]);
+      if (lane == 0) hid[u * S + j] = fmaxf(a + b1[j], 0.f);
+    }
   }
   __syncthreads();
-  for (int c = tid; c < C; c += 256) {
-    float acc = b2[c];
-    for (int j = 0; j < S; ++j) acc = fmaf(hid[j], __ldg(W2t + static_cast<size_t>(j) * C + c), acc);
-    scale[static_cast<size_t>(b) * C + c] = 1.0f / (1.0f + __expf(-acc));
+  const int c = blockIdx.y * 256 + tid;
+  if (c < C) {
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = b2[c];
+#pragma unroll 8
+    for (int j = 0; j < S; ++j) {
+      const float wv = __ldg(W2t + static_cast<size_t>(j) * C + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fmaf(hid[u * S + j], wv, acc[u]);
+    }
+    for (int u = 0; u < nb; ++u) scale[static_cast<size_t>(b0 + u) * C + c] = 1.0f / (1.0f + __expf(-acc[u]));
   }
 }
 

@@ -60,7 +60,7 @@ inline int num_sms() {
 
 template <int EPI, int MAX_BN>
 inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
-  using Cfg = GemmCfg<MAX_BN>;
+  using Cfg = GemmCfg<EPI, MAX_BN>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tc_kernel<EPI, MAX_BN>,

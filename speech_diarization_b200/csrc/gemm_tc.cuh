@@ -12,8 +12,10 @@
 // 128-byte swizzle; accumulators are f32 in TMEM, double-buffered so that the
 // epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2..5 = epilogue (each owns the TMEM lane quarter warp_idx % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue.
+// An epilogue warp may only touch the TMEM lane quarter warp_idx % 4, so two warps share each
+// quarter and split the tile's columns between them (one epilogue warp per scheduler was
+// latency-bound: a single warp cannot hide the TMEM-load -> math -> store dependency chain).
 //
 // Epilogues (template parameter EPI):
 //   EPI_F32   raw f32 store (unit tests)
@@ -36,17 +38,18 @@ namespace sd {
 constexpr int BM = 128;        // UMMA M: rows of the A tile = TMEM lanes
 constexpr int BK = 64;         // f16 elements per K chunk = one 128-byte swizzle span
 constexpr int UMMA_K = 16;     // K per tcgen05.mma for 16-bit operands
-constexpr int MAX_KITERS = 48; // 3072 / 64 (the MFA layer)
-constexpr int GEMM_THREADS = 192;
+constexpr int MAX_KITERS = 96; // 6144 / 64 (the per-utterance dense layers after pooling)
+constexpr int GEMM_THREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 
-enum { EPI_F32 = 0, EPI_TDNN = 1, EPI_POOL = 2, EPI_AFF = 3 };
+enum { EPI_F32 = 0, EPI_TDNN = 1, EPI_POOL = 2, EPI_AFF = 3, EPI_ATT = 4 };
 enum {
-  EF_RELU_BN = 1,   // x = relu(x + bias) * scale + shift
   EF_REFLECT = 2,   // store interior rows only and mirror them into the halo rows
-  EF_TANH = 4,      // tanh after BN (ASP attention TDNN)
-  EF_UTT_BIAS = 8,  // bias comes from a per-utterance table instead of `bias`
 };
+// EPI_TDNN : x = relu(acc + bias) * scale + shift                       (TDNNBlock tail)
+// EPI_ATT  : x = tanh(relu(acc + bias + utt_bias[b]) * scale + shift)   (ASP attention TDNN)
 
 struct KIter {
   int a_col;      // element column in A's tensor map
@@ -88,6 +91,7 @@ struct EpiParams {
   const float* gmean;  // [B, ld_gmean], first C entries of a row = mean
   int ld_gmean;
   float* pooled;       // [B, 2*C]: mean then std
+  __half* pooled_h;    // same, f16 (A operand of the final FC GEMM)
   int C;
   // EPI_AFF
   double* out_f64;  // optional second copy as f64 (AHC working matrix), same ld
@@ -96,6 +100,7 @@ struct EpiParams {
 struct alignas(64) GemmParams {
   CUtensorMap tmapA;
   CUtensorMap tmapB;
+  CUtensorMap tmapH;  // EPI_POOL only: the h activations, box = 64 channels x n_tile rows
   int num_m_blocks, num_n_blocks, num_kiters;
   int n_tile;      // UMMA N and rows of the B box
   int a_row_base;  // added to every A row coordinate (row-block sharding)
@@ -105,28 +110,34 @@ struct alignas(64) GemmParams {
   EpiParams epi;
 };
 
-template <int MAX_BN>
+template <int EPI, int MAX_BN>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;         // 16 KB
   static constexpr int B_BYTES = MAX_BN * BK * 2;     // 16 / 32 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (MAX_BN == 256) ? 4 : 6;
-  static constexpr int EPI_SMEM_FLOATS = 3 * 256;     // bias/scale/shift of one n block
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_FLOATS * 4 + 256 + 1024;
+  // EPI_POOL has only 2 k-iterations per tile and needs room for the staged h tiles
+  static constexpr int STAGES = (EPI == EPI_POOL) ? 2 : ((MAX_BN == 256) ? 4 : 6);
+  static constexpr int EPI_SMEM_FLOATS = 3 * 256;     // EPI_TDNN: bias/scale/shift of one n block
+  // EPI_POOL: two buffers of [2 chunks][n_tile rows][128 B] (n_tile <= 256 -> 64 KB each)
+  // EPI_POOL additionally needs 2 KB to combine the two column halves of the softmax statistics
+  static constexpr int EPI_REGION_BYTES = (EPI == EPI_POOL) ? 2 * 2 * MAX_BN * 128 + 2048 : EPI_SMEM_FLOATS * 4;
+  static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_REGION_BYTES + 256;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 };
 
 // ------------------------------------------------------------------ epilogues
 __device__ __forceinline__ void epi_named_barrier() {
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
 // raw f32
 __device__ __forceinline__ void epilogue_f32(const GemmParams& P, int m_blk, int n_blk,
-                                             uint32_t tmem_acc, int quarter, int lane) {
+                                             uint32_t tmem_acc, int quarter, int half, int lane) {
   const EpiParams& E = P.epi;
   const int r = m_blk * BM + quarter * 32 + lane;
   float* out = reinterpret_cast<float*>(E.out);
-  for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+  for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
     uint32_t v[16];
     __syncwarp();
     tmem_ld16(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
@@ -136,14 +147,17 @@ __device__ __forceinline__ void epilogue_f32(const GemmParams& P, int m_blk, int
       float* dst = out + static_cast<size_t>(r) * E.ld_out + E.out_col_off + col0;
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (col0 + j < E.N_cols) dst[j] = __uint_as_float(v[j]);
+        if (col0 + j < E.N_cols) dst[j] = __uint_as_float(v[j]) + (E.bias ? __ldg(E.bias + col0 + j) : 0.f);
     }
   }
 }
 
-// TDNN tail. `sp` = this n block's {bias, scale, shift} staged in shared memory.
+// TDNN tail. `sp` = this n block's {bias, scale, shift} staged in shared memory
+// (read as float4: 3/4 of a shared load per element).  ATT adds the per-utterance context
+// bias and the tanh of the attention TDNN; everything per-element is branch-free.
+template <bool ATT>
 __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, int n_blk,
-                                              uint32_t tmem_acc, int quarter, int lane,
+                                              uint32_t tmem_acc, int quarter, int half, int lane,
                                               const float* sp) {
   const EpiParams& E = P.epi;
   const int r = m_blk * BM + quarter * 32 + lane;
@@ -159,8 +173,8 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
     }
   }
   __half* out = reinterpret_cast<__half*>(E.out);
-  const float* ub = (E.flags & EF_UTT_BIAS) ? E.utt_bias + static_cast<size_t>(b) * E.N_cols : nullptr;
-  for (int c0 = 0; c0 < P.n_tile; c0 += 32) {
+  const float* ub = ATT ? E.utt_bias + static_cast<size_t>(valid ? b : 0) * E.N_cols : nullptr;
+  for (int c0 = half * 32; c0 < P.n_tile; c0 += 64) {
     uint32_t v[32];
     __syncwarp();
     tmem_ld32(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
@@ -168,14 +182,25 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
     if (!valid) continue;
     const int col0 = n_blk * P.n_tile + c0;  // column within this layer's output
     float x[32];
+    const float4* b4 = reinterpret_cast<const float4*>(sp + c0);
+    const float4* s4 = reinterpret_cast<const float4*>(sp + 256 + c0);
+    const float4* h4 = reinterpret_cast<const float4*>(sp + 512 + c0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float a = __uint_as_float(v[j]);
-      if (E.flags & EF_UTT_BIAS) a += __ldg(ub + col0 + j);
-      else a += sp[c0 + j];
-      if (E.flags & EF_RELU_BN) a = fmaxf(a, 0.f) * sp[256 + c0 + j] + sp[512 + c0 + j];
-      if (E.flags & EF_TANH) a = tanhf(a);
-      x[j] = a;
+    for (int q = 0; q < 8; ++q) {
+      float4 bb = b4[q];
+      const float4 ss = s4[q], hh = h4[q];
+      if (ATT) {
+        const float4 uu = __ldg(reinterpret_cast<const float4*>(ub + col0) + q);
+        bb.x += uu.x; bb.y += uu.y; bb.z += uu.z; bb.w += uu.w;
+      }
+      x[4 * q + 0] = fmaf(fmaxf(__uint_as_float(v[4 * q + 0]) + bb.x, 0.f), ss.x, hh.x);
+      x[4 * q + 1] = fmaf(fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y, 0.f), ss.y, hh.y);
+      x[4 * q + 2] = fmaf(fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z, 0.f), ss.z, hh.z);
+      x[4 * q + 3] = fmaf(fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w, 0.f), ss.w, hh.w);
+    }
+    if (ATT) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
     }
     uint4 pk[4];
 #pragma unroll
@@ -246,59 +271,109 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
 // Attentive statistics pooling. Tile rows = 128 channels, tile columns = the Tp
 // rows of utterance n_blk, so each thread owns one channel's logits over time.
 // The conv bias of the attention's output layer is constant over time and
-// cancels in the softmax, so it is never added.
+// cancels in the softmax, so it is never added.  The matching h tile
+// ([Tp rows][128 channels] f16) was staged in shared memory by TMA (128-byte
+// swizzle: 16-byte chunk index ^= row & 7), so the 151 per-thread reads of h are
+// shared-memory reads instead of latency-bound 2-byte global loads.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, int n_blk,
-                                              uint32_t tmem_acc, int quarter, int lane) {
+                                              uint32_t tmem_acc, int quarter, int half, int lane,
+                                              const uint8_t* hbuf, float4* xchg) {
   const EpiParams& E = P.epi;
-  const int ch = m_blk * BM + quarter * 32 + lane;
+  const int chl = quarter * 32 + lane;  // channel within the tile
+  const int ch = m_blk * BM + chl;
   const int b = n_blk;
   const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
   const bool chv = ch < E.C;
+  const float LOG2E = 1.4426950408889634f;
+  // this warp's share of the frames: 16-column chunks  half, half+2, ...
   // pass 1: max over interior frames
   float mx = -INFINITY;
-  for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+  for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
     uint32_t v[16];
     tmem_ld16(tbase + c0, v);
     tmem_ld_wait();
+    if (c0 >= E.H && c0 + 16 <= E.H + E.T) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int t = c0 + j - E.H;
-      if (t >= 0 && t < E.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+      for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int t = c0 + j - E.H;
+        if (t >= 0 && t < E.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
     }
   }
   // pass 2: softmax-weighted first/second moments about the global mean g
   const float g = chv ? E.gmean[static_cast<size_t>(b) * E.ld_gmean + ch] : 0.f;
-  const __half* hcol = E.h + static_cast<size_t>(b) * E.Tp * E.ld_h + (chv ? ch : 0);
+  const uint8_t* hchunk = hbuf + (chl >> 6) * (P.n_tile * 128) + (chl & 7) * 2;
+  const int c16 = (chl & 63) >> 3;
+  const float mxs = (mx == -INFINITY) ? 0.f : mx * LOG2E;  // a half with no interior frame
   float se = 0.f, s1 = 0.f, s2 = 0.f;
-  for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+  for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
     uint32_t v[16];
     tmem_ld16(tbase + c0, v);
     float xv[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int t = c0 + j - E.H;
-      xv[j] = (t >= 0 && t < E.T) ? __half2float(hcol[static_cast<size_t>(c0 + j) * E.ld_h]) : 0.f;
+      const int p = c0 + j;
+      xv[j] = __half2float(*reinterpret_cast<const __half*>(hchunk + p * 128 + ((c16 ^ (p & 7)) << 4))) - g;
     }
     tmem_ld_wait();
+    if (c0 >= E.H && c0 + 16 <= E.H + E.T) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int t = c0 + j - E.H;
-      if (t >= 0 && t < E.T) {
-        const float e = __expf(__uint_as_float(v[j]) - mx);
-        const float x = xv[j] - g;
+      for (int j = 0; j < 16; ++j) {
+        const float e = ex2_approx(fmaf(__uint_as_float(v[j]), LOG2E, -mxs));
         se += e;
-        s1 = fmaf(e, x, s1);
-        s2 = fmaf(e * x, x, s2);
+        const float ex = e * xv[j];
+        s1 += ex;
+        s2 = fmaf(ex, xv[j], s2);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int t = c0 + j - E.H;
+        if (t >= 0 && t < E.T) {
+          const float e = ex2_approx(fmaf(__uint_as_float(v[j]), LOG2E, -mxs));
+          se += e;
+          const float ex = e * xv[j];
+          s1 += ex;
+          s2 = fmaf(ex, xv[j], s2);
+        }
       }
     }
   }
-  if (chv) {
-    const float inv = 1.f / se;
-    const float m1 = s1 * inv;
-    const float var = fmaxf(s2 * inv - m1 * m1, 1e-12f);
-    E.pooled[static_cast<size_t>(b) * 2 * E.C + ch] = g + m1;
-    E.pooled[static_cast<size_t>(b) * 2 * E.C + E.C + ch] = sqrtf(var);
+  // combine the two column halves (half 1 -> shared -> half 0)
+  if (half == 1) xchg[chl] = make_float4(mx, se, s1, s2);
+  epi_named_barrier();
+  if (half == 0) {
+    const float4 o = xchg[chl];
+    const float M = fmaxf(mx, o.x);
+    const float fa = (mx == -INFINITY) ? 0.f : ex2_approx((mx - M) * LOG2E);
+    const float fb = (o.x == -INFINITY) ? 0.f : ex2_approx((o.x - M) * LOG2E);
+    se = se * fa + o.y * fb;
+    s1 = s1 * fa + o.z * fb;
+    s2 = s2 * fa + o.w * fb;
+    if (chv) {
+      const float inv = 1.f / se;
+      const float m1 = s1 * inv;
+      const float mean = g + m1;
+      const float sd = sqrtf(fmaxf(s2 * inv - m1 * m1, 1e-12f));
+      const size_t oo = static_cast<size_t>(b) * 2 * E.C + ch;
+      E.pooled[oo] = mean;
+      E.pooled[oo + E.C] = sd;
+      if (E.pooled_h) {
+        E.pooled_h[oo] = __float2half_rn(mean);
+        E.pooled_h[oo + E.C] = __float2half_rn(sd);
+      }
+    }
   }
+  epi_named_barrier();  // xchg may be overwritten by the next tile
 }
 
 // Cosine distance from the three split-f16 partial products:
@@ -306,12 +381,12 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
 //   S = slot0 + (slot1 + slot2) * 2^-11 ,  D = 1 - S      (f32, as sklearn computes it)
 // slot1 + slot2 is commutative, so D is exactly symmetric.
 __device__ __forceinline__ void epilogue_aff(const GemmParams& P, int m_blk, int n_blk,
-                                             uint32_t tmem_acc, int quarter, int lane) {
+                                             uint32_t tmem_acc, int quarter, int half, int lane) {
   const EpiParams& E = P.epi;
   const int r = m_blk * BM + quarter * 32 + lane;
   const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
   float* out = reinterpret_cast<float*>(E.out);
-  for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+  for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
     uint32_t v0[16], v1[16], v2[16];
     __syncwarp();
     tmem_ld16(tbase + c0, v0);
@@ -349,18 +424,23 @@ __device__ __forceinline__ void epilogue_aff(const GemmParams& P, int m_blk, int
 template <int EPI, int MAX_BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams P) {
-  using Cfg = GemmCfg<MAX_BN>;
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment is required by the 128-byte swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  float* epi_sp = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_sp + Cfg::EPI_SMEM_FLOATS);
+  using Cfg = GemmCfg<EPI, MAX_BN>;
+  // 1024-byte alignment is required by the 128-byte swizzle atoms.  Declaring it on the array
+  // (instead of rounding the pointer up by hand) keeps every derived pointer in the shared
+  // address space, so the epilogues' reads compile to LDS rather than generic loads.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* epi_region = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  float* epi_sp = reinterpret_cast<float*>(epi_region);  // EPI_TDNN: per-column constants
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_region + Cfg::EPI_REGION_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]
   uint64_t* empty_bar = bars + Cfg::STAGES;      // [STAGES]
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* hfull_bar = tempty_bar + 2;          // [2]  EPI_POOL: staged h tile landed
+  uint64_t* hempty_bar = hfull_bar + 2;          // [2]  EPI_POOL: epilogue done with it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty_bar + 2);
+  const uint32_t hbuf_bytes = 2u * static_cast<uint32_t>(P.n_tile) * 128u;  // EPI_POOL: one h tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -371,13 +451,16 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
     if (lane == 0) {
       tma_prefetch_desc(&P.tmapA);
       tma_prefetch_desc(&P.tmapB);
+      if (EPI == EPI_POOL) tma_prefetch_desc(&P.tmapH);
       for (int s = 0; s < Cfg::STAGES; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull_bar[s], 1);
-        mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+        mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
+        mbar_init(&hfull_bar[s], 1);
+        mbar_init(&hempty_bar[s], EPI_WARPS);
       }
       fence_barrier_init();
     }
@@ -396,9 +479,20 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
       const uint32_t tx = Cfg::A_BYTES + static_cast<uint32_t>(P.n_tile) * BK * 2;
       int stage = 0;
       uint32_t phase = 0;
+      int hs = 0;
+      uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / P.num_n_blocks;
         const int n_blk = tile - m_blk * P.num_n_blocks;
+        if (EPI == EPI_POOL) {
+          // the h tile this tile's epilogue will weight: 128 channels x n_tile rows, two 64-channel boxes
+          mbar_wait(&hempty_bar[hs], hphase ^ 1);
+          mbar_arrive_expect_tx(&hfull_bar[hs], hbuf_bytes);
+          uint8_t* hb = epi_region + hs * hbuf_bytes;
+          tma_load_2d(hb, &P.tmapH, &hfull_bar[hs], m_blk * BM, n_blk * P.n_tile);
+          tma_load_2d(hb + hbuf_bytes / 2, &P.tmapH, &hfull_bar[hs], m_blk * BM + BK, n_blk * P.n_tile);
+          if (++hs == 2) { hs = 0; hphase ^= 1; }
+        }
         for (int k = 0; k < P.num_kiters; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -445,17 +539,20 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the tile's column chunks it handles
     const int et = threadIdx.x - 64;
     int as = 0;
     uint32_t aphase = 0;
+    int hs = 0;
+    uint32_t hphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / P.num_n_blocks;
       const int n_blk = tile - m_blk * P.num_n_blocks;
-      if (EPI == EPI_TDNN) {
+      if (EPI == EPI_TDNN || EPI == EPI_ATT) {
         // stage this n block's per-column constants
         epi_named_barrier();  // previous tile's readers are done
-        for (int i = et; i < P.n_tile; i += 128) {
+        for (int i = et; i < P.n_tile; i += EPI_THREADS) {
           const int c = n_blk * P.n_tile + i;
           const bool ok = c < P.epi.N_cols;
           epi_sp[i] = (ok && P.epi.bias) ? P.epi.bias[c] : 0.f;
@@ -467,10 +564,18 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t acc = tmem_base + as * 256;
-      if (EPI == EPI_F32) epilogue_f32(P, m_blk, n_blk, acc, quarter, lane);
-      if (EPI == EPI_TDNN) epilogue_tdnn(P, m_blk, n_blk, acc, quarter, lane, epi_sp);
-      if (EPI == EPI_POOL) epilogue_pool(P, m_blk, n_blk, acc, quarter, lane);
-      if (EPI == EPI_AFF) epilogue_aff(P, m_blk, n_blk, acc, quarter, lane);
+      if (EPI == EPI_F32) epilogue_f32(P, m_blk, n_blk, acc, quarter, half, lane);
+      if (EPI == EPI_TDNN) epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp);
+      if (EPI == EPI_ATT) epilogue_tdnn<true>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp);
+      if (EPI == EPI_POOL) {
+        mbar_wait(&hfull_bar[hs], hphase);
+        epilogue_pool(P, m_blk, n_blk, acc, quarter, half, lane, epi_region + hs * hbuf_bytes,
+                      reinterpret_cast<float4*>(epi_region + 2 * 2 * MAX_BN * 128));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hempty_bar[hs]);
+        if (++hs == 2) { hs = 0; hphase ^= 1; }
+      }
+      if (EPI == EPI_AFF) epilogue_aff(P, m_blk, n_blk, acc, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
