@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -59,6 +60,7 @@ struct Program {     // launch parameters for one (B, T) shape
   int B = 0, T = 0, Tp = 0;
   long rows = 0;
   GemmParams block0, tdnn1[3], res[3][7], tdnn2[3], mfa, ctx, att, pool, fc;
+  GemmParams* chain_dev = nullptr;  // device copy of [3][9]: tdnn1, 7 x Res2Net, tdnn2 per block
 };
 
 }  // namespace
@@ -85,6 +87,10 @@ struct SdEcapaPlan {
   Program* last = nullptr;
   // optional per-stage timing (CUDA events on the caller's stream; bench.py's roofline leg)
   bool profile = false;
+  // SD_ECAPA_CHAIN=1 runs each block's tdnn1 -> 7 x Res2Net -> tdnn2 as ONE cooperative launch with grid
+  // barriers between the steps.  Measured slower than nine stream-ordered launches (0.735 vs 0.623 ms per
+  // block at B=512: the per-step pipeline fill/drain costs more than the launch gaps), so it is off.
+  bool use_chain = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   int forwards_profiled = 0;
@@ -203,7 +209,11 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     *out = &it->second;
     return SD_OK;
   }
-  if (p->programs.size() > 64) p->programs.clear();
+  if (p->programs.size() > 64) {
+    cudaDeviceSynchronize();  // launches that reference the cached descriptors may still be in flight
+    p->programs.clear();
+    p->last = nullptr;
+  }
   Program pr;
   pr.B = B;
   pr.T = T;
@@ -323,6 +333,18 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     P.epi.pooled_h = p->pooled_h;
     P.epi.C = C3;
   }
+  {
+    std::vector<GemmParams> chain;
+    for (int b = 0; b < 3; ++b) {
+      chain.push_back(pr.tdnn1[b]);
+      for (int i = 0; i < 7; ++i) chain.push_back(pr.res[b][i]);
+      chain.push_back(pr.tdnn2[b]);
+    }
+    void* d = nullptr;
+    SD_TRY(dev_alloc(p, &d, chain.size() * sizeof(GemmParams), false));
+    SD_CUDA_OK(cudaMemcpy(d, chain.data(), chain.size() * sizeof(GemmParams), cudaMemcpyHostToDevice));
+    pr.chain_dev = static_cast<GemmParams*>(d);
+  }
   auto ins = p->programs.emplace(key, pr);
   *out = &ins.first->second;
   return SD_OK;
@@ -355,11 +377,18 @@ int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStr
     const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
     const int ld_in = b == 0 ? C1 : C3;
     mark(p, st);
-    SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn1[b], st));
-    mark(p, st);
-    for (int i = 0; i < 7; ++i) SD_TRY(launch_gemm<EPI_TDNN>(pr.res[b][i], st));
-    mark(p, st);
-    SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn2[b], st));
+    if (p->use_chain) {
+      // tdnn1 -> 7 dependent Res2Net convs -> tdnn2 in ONE cooperative launch (grid barrier between steps)
+      SD_TRY((launch_gemm_chain<EPI_TDNN, 256>(pr.chain_dev + 9 * b, 9, st)));
+      mark(p, st);
+      mark(p, st);
+    } else {
+      SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn1[b], st));
+      mark(p, st);
+      for (int i = 0; i < 7; ++i) SD_TRY(launch_gemm<EPI_TDNN>(pr.res[b][i], st));
+      mark(p, st);
+      SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn2[b], st));
+    }
     mark(p, st);
     time_mean_kernel<<<dim3(C1 / 256, B), 128, 0, st>>>(p->w, C1, Tp, T, HALO, C1, p->se_mean);
     se_mlp_kernel<<<dim3((B + 3) / 4, C1 / 256), 256, 4 * (C1 + SE) * sizeof(float), st>>>(
@@ -419,6 +448,7 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   for (int i = 0; i < n_tensors; ++i) sd.m[names[i]] = {tensors[i], numels[i]};
   SdEcapaPlan* p = new SdEcapaPlan;
   p->max_batch = max_batch;
+  if (const char* e = getenv("SD_ECAPA_CHAIN")) p->use_chain = atoi(e) != 0;
   p->max_samples = max_samples;
   const int maxT = 1 + max_samples / 160;
   p->max_rows = (long)max_batch * tp_of(maxT);

@@ -87,6 +87,26 @@ inline int launch_gemm(const GemmParams& P, cudaStream_t stream) {
   return launch_gemm_t<EPI, 256>(P, stream);
 }
 
+// Cooperative launch of a chain of dependent GEMMs (gemm_chain_kernel); `dev_steps` is a device
+// array of num_steps GemmParams.  n_tile of every step must fit MAX_BN.
+template <int EPI, int MAX_BN>
+inline int launch_gemm_chain(const GemmParams* dev_steps, int num_steps, cudaStream_t stream) {
+  using Cfg = GemmCfg<EPI, MAX_BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_chain_kernel<EPI, MAX_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::SMEM_BYTES) != cudaSuccess)
+      return SD_ERR_CUDA;
+    attr_set = true;
+  }
+  void* args[] = {(void*)&dev_steps, (void*)&num_steps};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)gemm_chain_kernel<EPI, MAX_BN>, dim3(num_sms()),
+                                              dim3(GEMM_THREADS), args, Cfg::SMEM_BYTES, stream);
+  count_launch();
+  if (e != cudaSuccess) return fail(SD_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+  return SD_OK;
+}
+
 inline void init_params(GemmParams& P) {
   std::memset(&P, 0, sizeof(P));
   P.acc_slots = 1;

@@ -30,6 +30,7 @@
 //   EPI_AFF   cosine distance 1 - S from split-f16 partial products
 //             (diar_diag.py:215,219; anti_stick_diarize.py:176-177)
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda.h>
 #include "sd_ptx.cuh"
 
@@ -152,13 +153,34 @@ __device__ __forceinline__ void epilogue_f32(const GemmParams& P, int m_blk, int
   }
 }
 
+// Res2Net chain: fetch this thread's x_{i+1} values (add_src) for its (at most two) 32-column
+// chunks BEFORE waiting for the accumulator, so the global-load latency overlaps the MMAs.
+__device__ __forceinline__ void tdnn_prefetch(const GemmParams& P, int m_blk, int n_blk, int quarter,
+                                              int half, int lane, uint4 (&pre)[2][4]) {
+  const EpiParams& E = P.epi;
+  if (E.sum_out == nullptr) return;
+  const int r = m_blk * BM + quarter * 32 + lane;
+  if (r >= E.M_rows) return;
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci) {
+    const int c0 = half * 32 + ci * 64;
+    if (c0 < P.n_tile) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(
+          E.add_src + static_cast<size_t>(r) * E.ld_add + E.add_col_off + n_blk * P.n_tile + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pre[ci][q] = a4[q];  // plain (coherent) loads: in a chain, add_src was
+                                                        // written by an earlier step of the same kernel
+    }
+  }
+}
+
 // TDNN tail. `sp` = this n block's {bias, scale, shift} staged in shared memory
 // (read as float4: 3/4 of a shared load per element).  ATT adds the per-utterance context
 // bias and the tanh of the attention TDNN; everything per-element is branch-free.
 template <bool ATT>
 __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, int n_blk,
                                               uint32_t tmem_acc, int quarter, int half, int lane,
-                                              const float* sp) {
+                                              const float* sp, const uint4 (&pre)[2][4]) {
   const EpiParams& E = P.epi;
   const int r = m_blk * BM + quarter * 32 + lane;
   const int b = r / E.Tp;
@@ -234,12 +256,12 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
     if (E.sum_out != nullptr) {
       // next Res2Net input: x_{i+1} + y_i, built from the f16-rounded y_i the next conv
       // would otherwise have read back (keeps the sum bit-identical to an unfused chain).
-      const uint4* a4 = reinterpret_cast<const uint4*>(
-          E.add_src + static_cast<size_t>(r) * E.ld_add + E.add_col_off + col0);
+      // the x_{i+1} values were prefetched before the accumulator was waited for (tdnn_prefetch)
+      const int ci = (c0 >> 6) & 1;
       uint4 sk[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4 av = __ldg(a4 + q);
+        const uint4 av = ci ? pre[1][q] : pre[0][q];
         const __half2* ah = reinterpret_cast<const __half2*>(&av);
         const __half2* yh = reinterpret_cast<const __half2*>(&pk[q]);
         __half2 s[4];
@@ -421,46 +443,55 @@ __device__ __forceinline__ void epilogue_aff(const GemmParams& P, int m_blk, int
 }
 
 // --------------------------------------------------------------------- kernel
+struct GemmCtx {
+  uint8_t* smem;
+  uint8_t* epi_region;
+  uint64_t *full_bar, *empty_bar, *tfull_bar, *tempty_bar, *hfull_bar, *hempty_bar;
+  uint32_t tmem_base;
+  int warp, lane;
+};
+
+// Ring / accumulator positions.  Each role keeps its own copy; they stay in step because every
+// role walks the same tile and k-iteration sequence.  They persist across the steps of a chain.
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  int as = 0;
+  uint32_t aphase = 0;
+  int hs = 0;
+  uint32_t hphase = 0;
+};
+
 template <int EPI, int MAX_BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ GemmParams P) {
+__device__ __forceinline__ void gemm_setup(uint8_t* smem, GemmCtx& c) {
   using Cfg = GemmCfg<EPI, MAX_BN>;
-  // 1024-byte alignment is required by the 128-byte swizzle atoms.  Declaring it on the array
-  // (instead of rounding the pointer up by hand) keeps every derived pointer in the shared
-  // address space, so the epilogues' reads compile to LDS rather than generic loads.
-  extern __shared__ __align__(1024) uint8_t smem[];
+  // 1024-byte alignment is required by the 128-byte swizzle atoms.  It is declared on the array
+  // (instead of rounding the pointer up by hand) so every derived pointer stays in the shared
+  // address space and the epilogues' reads compile to LDS rather than generic loads.
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* epi_region = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-  float* epi_sp = reinterpret_cast<float*>(epi_region);  // EPI_TDNN: per-column constants
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_region + Cfg::EPI_REGION_BYTES);
-  uint64_t* full_bar = bars;                     // [STAGES]
-  uint64_t* empty_bar = bars + Cfg::STAGES;      // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;  // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint64_t* hfull_bar = tempty_bar + 2;          // [2]  EPI_POOL: staged h tile landed
-  uint64_t* hempty_bar = hfull_bar + 2;          // [2]  EPI_POOL: epilogue done with it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty_bar + 2);
-  const uint32_t hbuf_bytes = 2u * static_cast<uint32_t>(P.n_tile) * 128u;  // EPI_POOL: one h tile
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int num_tiles = P.num_m_blocks * P.num_n_blocks;
-  const int acc_stages = (P.acc_slots * P.n_tile <= 256) ? 2 : 1;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&P.tmapA);
-      tma_prefetch_desc(&P.tmapB);
-      if (EPI == EPI_POOL) tma_prefetch_desc(&P.tmapH);
+  c.smem = smem;
+  c.epi_region = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(c.epi_region + Cfg::EPI_REGION_BYTES);
+  c.full_bar = bars;                        // [STAGES]
+  c.empty_bar = bars + Cfg::STAGES;         // [STAGES]
+  c.tfull_bar = bars + 2 * Cfg::STAGES;     // [2]
+  c.tempty_bar = c.tfull_bar + 2;           // [2]
+  c.hfull_bar = c.tempty_bar + 2;           // [2]  EPI_POOL: staged h tile landed
+  c.hempty_bar = c.hfull_bar + 2;           // [2]  EPI_POOL: epilogue done with it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.hempty_bar + 2);
+  c.warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  if (c.warp == 0) {
+    if (c.lane == 0) {
       for (int s = 0; s < Cfg::STAGES; ++s) {
-        mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 1);
+        mbar_init(&c.full_bar[s], 1);
+        mbar_init(&c.empty_bar[s], 1);
       }
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&tfull_bar[s], 1);
-        mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
-        mbar_init(&hfull_bar[s], 1);
-        mbar_init(&hempty_bar[s], EPI_WARPS);
+        mbar_init(&c.tfull_bar[s], 1);
+        mbar_init(&c.tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
+        mbar_init(&c.hfull_bar[s], 1);
+        mbar_init(&c.hempty_bar[s], EPI_WARPS);
       }
       fence_barrier_init();
     }
@@ -471,55 +502,73 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  c.tmem_base = *tmem_slot;
+}
+
+__device__ __forceinline__ void gemm_teardown(const GemmCtx& c) {
+  tc_fence_before();
+  __syncthreads();
+  if (c.warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(c.tmem_base, TMEM_COLS);
+  }
+}
+
+// One GEMM: every role walks this CTA's tiles (tile = blockIdx.x, + gridDim.x, ...).
+template <int EPI, int MAX_BN>
+__device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, PipeState& ps) {
+  using Cfg = GemmCfg<EPI, MAX_BN>;
+  uint8_t* const smem = c.smem;
+  uint8_t* const epi_region = c.epi_region;
+  float* const epi_sp = reinterpret_cast<float*>(epi_region);  // EPI_TDNN: per-column constants
+  const uint32_t hbuf_bytes = 2u * static_cast<uint32_t>(P.n_tile) * 128u;  // EPI_POOL: one h tile
+  const int warp = c.warp, lane = c.lane;
+  const int num_tiles = P.num_m_blocks * P.num_n_blocks;
+  const int acc_stages = (P.acc_slots * P.n_tile <= 256) ? 2 : 1;
+  const uint32_t tmem_base = c.tmem_base;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      tma_prefetch_desc(&P.tmapA);
+      tma_prefetch_desc(&P.tmapB);
+      if (EPI == EPI_POOL) tma_prefetch_desc(&P.tmapH);
       const uint32_t tx = Cfg::A_BYTES + static_cast<uint32_t>(P.n_tile) * BK * 2;
-      int stage = 0;
-      uint32_t phase = 0;
-      int hs = 0;
-      uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / P.num_n_blocks;
         const int n_blk = tile - m_blk * P.num_n_blocks;
         if (EPI == EPI_POOL) {
           // the h tile this tile's epilogue will weight: 128 channels x n_tile rows, two 64-channel boxes
-          mbar_wait(&hempty_bar[hs], hphase ^ 1);
-          mbar_arrive_expect_tx(&hfull_bar[hs], hbuf_bytes);
-          uint8_t* hb = epi_region + hs * hbuf_bytes;
-          tma_load_2d(hb, &P.tmapH, &hfull_bar[hs], m_blk * BM, n_blk * P.n_tile);
-          tma_load_2d(hb + hbuf_bytes / 2, &P.tmapH, &hfull_bar[hs], m_blk * BM + BK, n_blk * P.n_tile);
-          if (++hs == 2) { hs = 0; hphase ^= 1; }
+          mbar_wait(&c.hempty_bar[ps.hs], ps.hphase ^ 1);
+          mbar_arrive_expect_tx(&c.hfull_bar[ps.hs], hbuf_bytes);
+          uint8_t* hb = epi_region + ps.hs * hbuf_bytes;
+          tma_load_2d(hb, &P.tmapH, &c.hfull_bar[ps.hs], m_blk * BM, n_blk * P.n_tile);
+          tma_load_2d(hb + hbuf_bytes / 2, &P.tmapH, &c.hfull_bar[ps.hs], m_blk * BM + BK, n_blk * P.n_tile);
+          if (++ps.hs == 2) { ps.hs = 0; ps.hphase ^= 1; }
         }
         for (int k = 0; k < P.num_kiters; ++k) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], tx);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &P.tmapA, &full_bar[stage], P.kit[k].a_col,
+          mbar_wait(&c.empty_bar[ps.stage], ps.phase ^ 1);
+          mbar_arrive_expect_tx(&c.full_bar[ps.stage], tx);
+          uint8_t* sa = smem + ps.stage * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &P.tmapA, &c.full_bar[ps.stage], P.kit[k].a_col,
                       P.a_row_base + m_blk * BM + P.kit[k].a_row_off);
-          tma_load_2d(sa + Cfg::A_BYTES, &P.tmapB, &full_bar[stage], P.kit[k].b_col,
+          tma_load_2d(sa + Cfg::A_BYTES, &P.tmapB, &c.full_bar[ps.stage], P.kit[k].b_col,
                       n_blk * P.n_tile);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (++ps.stage == Cfg::STAGES) { ps.stage = 0; ps.phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait(&c.tempty_bar[ps.as], ps.aphase ^ 1);
         tc_fence_after();
-        const uint32_t acc = tmem_base + as * 256;
+        const uint32_t acc = tmem_base + ps.as * 256;
         for (int k = 0; k < P.num_kiters; ++k) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&c.full_bar[ps.stage], ps.phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(smem + ps.stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
           const uint64_t da = make_smem_desc_sw128(a_addr);
           const uint64_t db = make_smem_desc_sw128(b_addr);
@@ -530,11 +579,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
             umma_f16(d_addr, da + 2 * kk, db + 2 * kk, P.idesc,
                      (P.kit[k].accum | kk) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(&c.empty_bar[ps.stage]);  // frees the smem slot once these MMAs retire
+          if (++ps.stage == Cfg::STAGES) { ps.stage = 0; ps.phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
-        if (++as == acc_stages) { as = 0; aphase ^= 1; }
+        umma_commit(&c.tfull_bar[ps.as]);  // accumulator complete -> epilogue
+        if (++ps.as == acc_stages) { ps.as = 0; ps.aphase ^= 1; }
       }
     }
   } else {
@@ -542,10 +591,6 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;    // which half of the tile's column chunks it handles
     const int et = threadIdx.x - 64;
-    int as = 0;
-    uint32_t aphase = 0;
-    int hs = 0;
-    uint32_t hphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / P.num_n_blocks;
       const int n_blk = tile - m_blk * P.num_n_blocks;
@@ -553,42 +598,74 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
         // stage this n block's per-column constants
         epi_named_barrier();  // previous tile's readers are done
         for (int i = et; i < P.n_tile; i += EPI_THREADS) {
-          const int c = n_blk * P.n_tile + i;
-          const bool ok = c < P.epi.N_cols;
-          epi_sp[i] = (ok && P.epi.bias) ? P.epi.bias[c] : 0.f;
-          epi_sp[256 + i] = (ok && P.epi.scale) ? P.epi.scale[c] : 1.f;
-          epi_sp[512 + i] = (ok && P.epi.shift) ? P.epi.shift[c] : 0.f;
+          const int col = n_blk * P.n_tile + i;
+          const bool ok = col < P.epi.N_cols;
+          epi_sp[i] = (ok && P.epi.bias) ? P.epi.bias[col] : 0.f;
+          epi_sp[256 + i] = (ok && P.epi.scale) ? P.epi.scale[col] : 1.f;
+          epi_sp[512 + i] = (ok && P.epi.shift) ? P.epi.shift[col] : 0.f;
         }
         epi_named_barrier();
       }
-      mbar_wait(&tfull_bar[as], aphase);
+      uint4 pre[2][4];
+      if (EPI == EPI_TDNN) tdnn_prefetch(P, m_blk, n_blk, quarter, half, lane, pre);
+      mbar_wait(&c.tfull_bar[ps.as], ps.aphase);
       tc_fence_after();
-      const uint32_t acc = tmem_base + as * 256;
+      const uint32_t acc = tmem_base + ps.as * 256;
       if (EPI == EPI_F32) epilogue_f32(P, m_blk, n_blk, acc, quarter, half, lane);
-      if (EPI == EPI_TDNN) epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp);
-      if (EPI == EPI_ATT) epilogue_tdnn<true>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp);
+      if (EPI == EPI_TDNN) epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre);
+      if (EPI == EPI_ATT) epilogue_tdnn<true>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre);
       if (EPI == EPI_POOL) {
-        mbar_wait(&hfull_bar[hs], hphase);
-        epilogue_pool(P, m_blk, n_blk, acc, quarter, half, lane, epi_region + hs * hbuf_bytes,
+        mbar_wait(&c.hfull_bar[ps.hs], ps.hphase);
+        epilogue_pool(P, m_blk, n_blk, acc, quarter, half, lane, epi_region + ps.hs * hbuf_bytes,
                       reinterpret_cast<float4*>(epi_region + 2 * 2 * MAX_BN * 128));
         __syncwarp();
-        if (lane == 0) mbar_arrive(&hempty_bar[hs]);
-        if (++hs == 2) { hs = 0; hphase ^= 1; }
+        if (lane == 0) mbar_arrive(&c.hempty_bar[ps.hs]);
+        if (++ps.hs == 2) { ps.hs = 0; ps.hphase ^= 1; }
       }
       if (EPI == EPI_AFF) epilogue_aff(P, m_blk, n_blk, acc, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (++as == acc_stages) { as = 0; aphase ^= 1; }
+      if (lane == 0) mbar_arrive(&c.tempty_bar[ps.as]);
+      if (++ps.as == acc_stages) { ps.as = 0; ps.aphase ^= 1; }
     }
   }
+}
 
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+template <int EPI, int MAX_BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  GemmCtx c;
+  PipeState ps;
+  gemm_setup<EPI, MAX_BN>(smem, c);
+  gemm_run<EPI, MAX_BN>(P, c, ps);
+  gemm_teardown(c);
+}
+
+// A CHAIN of dependent GEMMs in one cooperative launch: step s+1 reads what step s wrote
+// (Res2Net: y_i = TDNN_i(x_i + y_{i-1}); around it the block's two 1x1 TDNNs).  Between steps
+// the whole grid synchronises; the generic-proxy stores of the epilogues are made visible to
+// the next step's TMA loads (async proxy) by fence.proxy.async on both sides of the barrier.
+// Barriers, TMEM and the smem ring are set up once; the pipeline positions carry over.
+// `steps` lives in global memory (TMA descriptors included; 64-byte aligned).
+template <int EPI, int MAX_BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_chain_kernel(const GemmParams* __restrict__ steps, int num_steps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  GemmCtx c;
+  PipeState ps;
+  gemm_setup<EPI, MAX_BN>(smem, c);
+  for (int s = 0; s < num_steps; ++s) {
+    gemm_run<EPI, MAX_BN>(steps[s], c, ps);
+    if (s + 1 < num_steps) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __threadfence();
+      grid.sync();
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
   }
+  gemm_teardown(c);
 }
 
 }  // namespace sd
