@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "gemm_tc.cuh"
 #include "sd_status.h"
 
@@ -47,6 +48,24 @@ inline int make_tmap_f16(CUtensorMap* m, const void* base, long rows, long cols,
   return r == CUDA_SUCCESS ? SD_OK : SD_ERR_DRIVER;
 }
 
+// 3-D f16 view for REFLECT-layer stores: {channels, T interior frames, utterances}.  `base` is the
+// activation tensor [B*Tp, ld]; element (c, t, b) lives at base + ((b*Tp + H + t) * ld + c).
+// Boxes are 64 channels x 128 frames x 1 utterance; frames outside [0, T) are clipped on store.
+inline int make_tmap_f16_interior(CUtensorMap* m, const void* base, long ld, int Tp, int T, int H, int B) {
+  PFN_tmapEncodeTiled enc = get_tmap_encoder();
+  if (!enc) return SD_ERR_DRIVER;
+  const char* p = static_cast<const char*>(base) + static_cast<size_t>(H) * ld * 2;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld * 2) % 16) return SD_ERR_ARG;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(Tp) * ld * 2};
+  cuuint32_t box[3] = {BK, BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<char*>(p), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SD_OK : SD_ERR_DRIVER;
+}
+
 inline int num_sms() {
   static int n = 0;
   if (!n) {
@@ -74,7 +93,13 @@ inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_tc_kernel<EPI, MAX_BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(P);
   count_launch();
-  return cudaGetLastError() == cudaSuccess ? SD_OK : SD_ERR_CUDA;
+  cudaError_t e = cudaGetLastError();
+  static const bool sync_debug = getenv("SD_SYNC_DEBUG") != nullptr;  // localise a faulting launch
+  if (e == cudaSuccess && sync_debug) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess)
+    return fail(SD_ERR_CUDA, "gemm_tc_kernel<EPI=%d,MAX_BN=%d> n_tile=%d kiters=%d tiles=%d flags=%d: %s", EPI, MAX_BN,
+                P.n_tile, P.num_kiters, tiles, P.epi.flags, cudaGetErrorString(e));
+  return SD_OK;
 }
 
 // Chooses the shared-memory configuration from n_tile.

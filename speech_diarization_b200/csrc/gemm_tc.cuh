@@ -117,13 +117,17 @@ struct GemmCfg {
   static constexpr int B_BYTES = MAX_BN * BK * 2;     // 16 / 32 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // EPI_POOL has only 2 k-iterations per tile and needs room for the staged h tiles
-  static constexpr int STAGES = (EPI == EPI_POOL) ? 2 : ((MAX_BN == 256) ? 4 : 6);
+  // EPI_TDNN/ATT stage the f16 output tile (and the Res2Net sum tile) in 64 KB of shared memory for
+  // a coalesced write-out, which leaves room for 3 (MAX_BN 256) / 4 (MAX_BN 128) operand stages.
+  static constexpr bool STAGED_OUT = (EPI == EPI_TDNN || EPI == EPI_ATT);
+  static constexpr int OUT_STAGE_BYTES = STAGED_OUT ? 65536 : 0;
+  static constexpr int STAGES = (EPI == EPI_POOL) ? 2 : (STAGED_OUT ? ((MAX_BN == 256) ? 3 : 4) : ((MAX_BN == 256) ? 4 : 6));
   static constexpr int EPI_SMEM_FLOATS = 3 * 256;     // EPI_TDNN: bias/scale/shift of one n block
   // EPI_POOL: two buffers of [2 chunks][n_tile rows][128 B] (n_tile <= 256 -> 64 KB each)
   // EPI_POOL additionally needs 2 KB to combine the two column halves of the softmax statistics
   static constexpr int EPI_REGION_BYTES = (EPI == EPI_POOL) ? 2 * 2 * MAX_BN * 128 + 2048 : EPI_SMEM_FLOATS * 4;
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_REGION_BYTES + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + EPI_REGION_BYTES + 256;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 };
 
@@ -180,28 +184,23 @@ __device__ __forceinline__ void tdnn_prefetch(const GemmParams& P, int m_blk, in
 template <bool ATT>
 __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, int n_blk,
                                               uint32_t tmem_acc, int quarter, int half, int lane,
-                                              const float* sp, const uint4 (&pre)[2][4]) {
+                                              const float* sp, const uint4 (&pre)[2][4],
+                                              uint8_t* stage_out) {
   const EpiParams& E = P.epi;
-  const int r = m_blk * BM + quarter * 32 + lane;
-  const int b = r / E.Tp;
-  const int t = r - b * E.Tp - E.H;
-  bool valid = r < E.M_rows;
-  int r2 = -1, r3 = -1;  // mirrored halo rows
-  if (E.flags & EF_REFLECT) {
-    valid = valid && t >= 0 && t < E.T;
-    if (valid) {
-      if (t >= 1 && t <= E.H) r2 = b * E.Tp + E.H - t;
-      if (t >= E.T - 1 - E.H && t <= E.T - 2) r3 = b * E.Tp + E.H + 2 * (E.T - 1) - t;
-    }
-  }
-  __half* out = reinterpret_cast<__half*>(E.out);
-  const float* ub = ATT ? E.utt_bias + static_cast<size_t>(valid ? b : 0) * E.N_cols : nullptr;
+  const int rl = quarter * 32 + lane;  // row within the tile
+  const int r = m_blk * BM + rl;
+  const float* ub = ATT ? E.utt_bias + static_cast<size_t>(r < E.M_rows ? r / E.Tp : 0) * E.N_cols : nullptr;
+  // staging tile: [64-column chunk][128 rows][128 B], 16-byte pieces XOR-swizzled by (row & 7) —
+  // the layout a SWIZZLE_128B tensor map expects, and conflict-free for one-row-per-lane writes.
+  uint8_t* srow = stage_out + rl * 128;
+  const int sw = rl & 7;
+  uint8_t* sum_stage = stage_out + 32768;  // Res2Net sum tile (n_tile = 128: two 16 KB chunks each)
   for (int c0 = half * 32; c0 < P.n_tile; c0 += 64) {
     uint32_t v[32];
     __syncwarp();
     tmem_ld32(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
     tmem_ld_wait();
-    if (!valid) continue;
+    if (E.flags & 64) continue;  // TIMING PROBE ONLY (SD_DEBUG_EPI=1): skip the epilogue math and stores
     const int col0 = n_blk * P.n_tile + c0;  // column within this layer's output
     float x[32];
     const float4* b4 = reinterpret_cast<const float4*>(sp + c0);
@@ -232,26 +231,14 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
       pk[q].z = pack_half2(x[8 * q + 4], x[8 * q + 5]);
       pk[q].w = pack_half2(x[8 * q + 6], x[8 * q + 7]);
     }
-    const size_t coff = static_cast<size_t>(E.out_col_off + col0);
+    if (E.flags & 128) continue;  // TIMING PROBE ONLY (SD_DEBUG_EPI=2): math but no stores
+    // -> staging (every row, valid or not: tdnn_writeout skips what must not be written)
+    const int chunk = c0 >> 6;           // 64-column chunk of the tile
+    const int p0 = (c0 >> 5 & 1) * 4;    // first 16-byte piece of this 32-column run inside the 128 B row
     {
-      uint4* d = reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * E.ld_out + coff);
+      uint8_t* d = srow + chunk * 16384;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) d[q] = pk[q];
-    }
-    if (r2 >= 0) {
-      uint4* d = reinterpret_cast<uint4*>(out + static_cast<size_t>(r2) * E.ld_out + coff);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) d[q] = pk[q];
-    }
-    if (r3 >= 0) {
-      uint4* d = reinterpret_cast<uint4*>(out + static_cast<size_t>(r3) * E.ld_out + coff);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) d[q] = pk[q];
-    }
-    if (E.out2 != nullptr && col0 < E.out2_cols) {
-      uint4* d = reinterpret_cast<uint4*>(E.out2 + static_cast<size_t>(r) * E.ld_out2 + col0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) d[q] = pk[q];
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(d + (((p0 + q) ^ sw) << 4)) = pk[q];
     }
     if (E.sum_out != nullptr) {
       // next Res2Net input: x_{i+1} + y_i, built from the f16-rounded y_i the next conv
@@ -264,27 +251,71 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
         const uint4 av = ci ? pre[1][q] : pre[0][q];
         const __half2* ah = reinterpret_cast<const __half2*>(&av);
         const __half2* yh = reinterpret_cast<const __half2*>(&pk[q]);
-        __half2 s[4];
+        __half2 sh[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float2 fa = __half22float2(ah[e]);
           float2 fy = __half22float2(yh[e]);
-          s[e] = __floats2half2_rn(fa.x + fy.x, fa.y + fy.y);
+          sh[e] = __floats2half2_rn(fa.x + fy.x, fa.y + fy.y);
         }
-        sk[q] = *reinterpret_cast<uint4*>(s);
+        sk[q] = *reinterpret_cast<uint4*>(sh);
       }
-      uint4* d = reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r) * E.ld_sum + col0);
+      {
+        uint8_t* d = sum_stage + rl * 128 + chunk * 16384;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) d[q] = sk[q];
-      if (r2 >= 0) {
-        uint4* d2 = reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r2) * E.ld_sum + col0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) d2[q] = sk[q];
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(d + (((p0 + q) ^ sw) << 4)) = sk[q];
       }
-      if (r3 >= 0) {
-        uint4* d3 = reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r3) * E.ld_sum + col0);
+    }
+  }
+}
+
+// Write-out of the staged tile by all 256 epilogue threads: 8 lanes cover one 128-byte row chunk,
+// so every store instruction writes four complete 128-byte lines (the direct one-row-per-thread
+// stores issued 16-byte pieces of 32 different lines per instruction and cost ~25% of the whole
+// forward in L2 transactions).  Halo / padding rows are skipped per row and the reflect mirrors
+// are written from the same registers.  (TMA tensor stores were tried first: they clip at the
+// upper tensor bound but FAULT on negative start coordinates, which the halo clipping needs —
+// tools/micro/tma_store_test.cu.)
+__device__ __forceinline__ void tdnn_writeout(const GemmParams& P, int m_blk, int n_blk,
+                                              const uint8_t* stage_out, int et) {
+  const EpiParams& E = P.epi;
+  if (E.flags & (64 | 128 | 256)) return;  // TIMING/DEBUG PROBES (SD_DEBUG_EPI)
+  const int sub = et & 7;    // 16-byte piece of the 128-byte row chunk
+  const int rsub = et >> 3;  // row within a 32-row pass
+  const int nchunks = P.n_tile >> 6;
+  __half* out = reinterpret_cast<__half*>(E.out);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) d3[q] = sk[q];
+  for (int pass = 0; pass < 4; ++pass) {
+    const int rl = pass * 32 + rsub;
+    const int r = m_blk * BM + rl;
+    if (r >= E.M_rows) continue;
+    bool valid = true;
+    int r2 = -1, r3 = -1;
+    if (E.flags & EF_REFLECT) {
+      const int b = r / E.Tp;
+      const int t = r - b * E.Tp - E.H;
+      valid = t >= 0 && t < E.T;
+      if (valid) {
+        if (t >= 1 && t <= E.H) r2 = b * E.Tp + E.H - t;
+        if (t >= E.T - 1 - E.H && t <= E.T - 2) r3 = b * E.Tp + E.H + 2 * (E.T - 1) - t;
+      }
+    }
+    if (!valid) continue;
+    const uint8_t* srow = stage_out + rl * 128 + ((sub ^ (rl & 7)) << 4);
+    for (int j = 0; j < nchunks; ++j) {
+      const int col = n_blk * P.n_tile + j * 64 + sub * 8;
+      const uint4 val = *reinterpret_cast<const uint4*>(srow + j * 16384);
+      const size_t coff = static_cast<size_t>(E.out_col_off + col);
+      *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * E.ld_out + coff) = val;
+      if (r2 >= 0) *reinterpret_cast<uint4*>(out + static_cast<size_t>(r2) * E.ld_out + coff) = val;
+      if (r3 >= 0) *reinterpret_cast<uint4*>(out + static_cast<size_t>(r3) * E.ld_out + coff) = val;
+      if (E.out2 != nullptr && col < E.out2_cols)
+        *reinterpret_cast<uint4*>(E.out2 + static_cast<size_t>(r) * E.ld_out2 + col) = val;
+      if (E.sum_out != nullptr) {
+        const uint4 sv = *reinterpret_cast<const uint4*>(srow + 32768 + j * 16384);
+        *reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r) * E.ld_sum + col) = sv;
+        if (r2 >= 0) *reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r2) * E.ld_sum + col) = sv;
+        if (r3 >= 0) *reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r3) * E.ld_sum + col) = sv;
       }
     }
   }
@@ -470,7 +501,7 @@ __device__ __forceinline__ void gemm_setup(uint8_t* smem, GemmCtx& c) {
   // address space and the epilogues' reads compile to LDS rather than generic loads.
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   c.smem = smem;
-  c.epi_region = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  c.epi_region = smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::OUT_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(c.epi_region + Cfg::EPI_REGION_BYTES);
   c.full_bar = bars;                        // [STAGES]
   c.empty_bar = bars + Cfg::STAGES;         // [STAGES]
@@ -520,6 +551,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
   using Cfg = GemmCfg<EPI, MAX_BN>;
   uint8_t* const smem = c.smem;
   uint8_t* const epi_region = c.epi_region;
+  uint8_t* const stage_out = smem + Cfg::STAGES * Cfg::STAGE_BYTES;  // EPI_TDNN/ATT output staging (64 KB)
   float* const epi_sp = reinterpret_cast<float*>(epi_region);  // EPI_TDNN: per-column constants
   const uint32_t hbuf_bytes = 2u * static_cast<uint32_t>(P.n_tile) * 128u;  // EPI_POOL: one h tile
   const int warp = c.warp, lane = c.lane;
@@ -591,12 +623,14 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;    // which half of the tile's column chunks it handles
     const int et = threadIdx.x - 64;
+    int last_n_blk = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / P.num_n_blocks;
       const int n_blk = tile - m_blk * P.num_n_blocks;
-      if (EPI == EPI_TDNN || EPI == EPI_ATT) {
-        // stage this n block's per-column constants
-        epi_named_barrier();  // previous tile's readers are done
+      if ((EPI == EPI_TDNN || EPI == EPI_ATT) && n_blk != last_n_blk) {
+        // stage this n block's per-column constants (the previous tile's readers all passed the
+        // "staging complete" barrier below, so the table may be overwritten)
+        last_n_blk = n_blk;
         for (int i = et; i < P.n_tile; i += EPI_THREADS) {
           const int col = n_blk * P.n_tile + i;
           const bool ok = col < P.epi.N_cols;
@@ -612,8 +646,11 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       tc_fence_after();
       const uint32_t acc = tmem_base + ps.as * 256;
       if (EPI == EPI_F32) epilogue_f32(P, m_blk, n_blk, acc, quarter, half, lane);
-      if (EPI == EPI_TDNN) epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre);
-      if (EPI == EPI_ATT) epilogue_tdnn<true>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre);
+      if (EPI == EPI_TDNN || EPI == EPI_ATT) {
+        epi_named_barrier();  // every thread has finished writing out the previous tile's staging
+        if (EPI == EPI_TDNN) epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre, stage_out);
+        if (EPI == EPI_ATT) epilogue_tdnn<true>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre, stage_out);
+      }
       if (EPI == EPI_POOL) {
         mbar_wait(&c.hfull_bar[ps.hs], ps.hphase);
         epilogue_pool(P, m_blk, n_blk, acc, quarter, half, lane, epi_region + ps.hs * hbuf_bytes,
@@ -625,8 +662,12 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       if (EPI == EPI_AFF) epilogue_aff(P, m_blk, n_blk, acc, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&c.tempty_bar[ps.as]);
+      if (lane == 0) mbar_arrive(&c.tempty_bar[ps.as]);  // TMEM drained: the next tile's MMAs may start
       if (++ps.as == acc_stages) { ps.as = 0; ps.aphase ^= 1; }
+      if (EPI == EPI_TDNN || EPI == EPI_ATT) {
+        epi_named_barrier();   // staging tile complete
+        tdnn_writeout(P, m_blk, n_blk, stage_out, et);
+      }
     }
   }
 }
