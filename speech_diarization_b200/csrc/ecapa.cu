@@ -80,7 +80,7 @@ struct SdEcapaPlan {
   // activations
   __half *feats = nullptr, *x0 = nullptr, *cat = nullptr, *u = nullptr, *v = nullptr, *w = nullptr;
   __half *s[2] = {nullptr, nullptr}, *h = nullptr, *attn = nullptr;
-  float *raw = nullptr, *se_mean = nullptr, *se_scale = nullptr, *stats = nullptr;
+  float *raw = nullptr, *se_mean = nullptr, *se_hid = nullptr, *se_scale = nullptr, *stats = nullptr;
   float *uttbias = nullptr, *pooled = nullptr, *emb_tmp = nullptr;
   __half *stats_h = nullptr, *pooled_h = nullptr;
   std::map<std::pair<int, int>, Program> programs;
@@ -304,17 +304,18 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   {
     GemmParams& P = pr.pool;
     init_params(P);
-    if (pr.Tp > 256)
-      return fail(SD_ERR_UNSUPPORTED,
-                  "windows longer than %d frames (%.2f s) are not supported by the fused pooling "
-                  "kernel yet (T=%d)", 256 - 2 * HALO, (256 - 2 * HALO) * 0.01, T);
+    // frames per chunk: the whole utterance when it fits one UMMA N (<= 256), else 256-row chunks
+    // with the softmax statistics carried across chunks (online softmax)
+    const int chunk = pr.Tp <= 256 ? pr.Tp : 256;
     SD_TRY(make_tmap_f16(&P.tmapA, p->Wa2, C3, ATT, ATT, BM));
-    SD_TRY(make_tmap_f16(&P.tmapB, p->attn, R, ATT, ATT, pr.Tp));
-    SD_TRY(make_tmap_f16(&P.tmapH, p->h, R, C3, C3, pr.Tp));
+    SD_TRY(make_tmap_f16(&P.tmapB, p->attn, R, ATT, ATT, chunk));
+    SD_TRY(make_tmap_f16(&P.tmapH, p->h, R, C3, C3, chunk));
     P.num_m_blocks = C3 / BM;
     P.num_n_blocks = B;
-    P.n_tile = pr.Tp;
-    P.idesc = make_idesc_f16(pr.Tp, 0);
+    P.n_tile = chunk;
+    P.n_sub = (pr.Tp + chunk - 1) / chunk;
+    P.b_row_stride = pr.Tp;
+    P.idesc = make_idesc_f16(chunk, 0);
     for (int c = 0; c < ATT / BK; ++c) {
       P.kit[c].a_col = c * BK;
       P.kit[c].b_col = c * BK;
@@ -392,14 +393,16 @@ int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStr
     }
     mark(p, st);
     time_mean_kernel<<<dim3(C1 / 256, B), 128, 0, st>>>(p->w, C1, Tp, T, HALO, C1, p->se_mean);
-    se_mlp_kernel<<<dim3((B + 3) / 4, C1 / 256), 256, 4 * (C1 + SE) * sizeof(float), st>>>(
-        p->se_mean, p->blk[b].se_w1, p->blk[b].se_b1, p->blk[b].se_w2t, p->blk[b].se_b2, B, C1, SE, p->se_scale);
+    se_hidden_kernel<<<dim3((B + 3) / 4, SE / 32), 256, 4 * C1 * sizeof(float), st>>>(
+        p->se_mean, p->blk[b].se_w1, p->blk[b].se_b1, B, C1, SE, p->se_hid);
+    se_scale_kernel<<<dim3((B + 3) / 4, C1 / 256), 256, 0, st>>>(p->se_hid, p->blk[b].se_w2t, p->blk[b].se_b2, B,
+                                                                  C1, SE, p->se_scale);
     const long vecs = R * (C1 / 8);
     const int grid = (int)((vecs + 255) / 256 < 148L * 16 ? (vecs + 255) / 256 : 148L * 16);
     se_apply_kernel<<<grid, 256, 0, st>>>(p->w, C1, p->se_scale, in, ld_in, p->cat + (size_t)b * C1, C3, R,
                                           Tp, C1);
     SD_CUDA_OK(cudaGetLastError());
-    count_launch(3);
+    count_launch(4);
   }
   mark(p, st);
   SD_TRY(launch_gemm<EPI_TDNN>(pr.mfa, st));
@@ -537,6 +540,7 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
     const size_t MB = (size_t)p->max_rows / tp_of(2 * HALO + 2) + 1;  // most utterances any shape can have
     SD_TRY(dev_alloc(p, (void**)&p->se_mean, MB * C1 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->se_scale, MB * C1 * 4, true));
+    SD_TRY(dev_alloc(p, (void**)&p->se_hid, MB * SE * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->stats, MB * 2 * C3 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->uttbias, MB * ATT * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->pooled, MB * 2 * C3 * 4, true));

@@ -100,57 +100,69 @@ time_mean_std_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H,
   }
 }
 
-// SE excitation: scale[b] = sigmoid(W2 relu(W1 mean[b] + b1) + b2).
-// W1 [S][C] row-major, W2t [S][C] (= conv2 weight transposed).  One CTA handles 4 utterances (the
-// weights are read from L2 once per 4) and one 256-channel slice of the output; the cheap hidden
-// layer is recomputed by each of the C/256 slices.  grid (ceil(B/4), C/256), block 256,
-// dynamic smem 4*(C+S) floats.
+// SE excitation, layer 1: hid[b, j] = relu(W1[j, :] . mean[b, :] + b1[j]).   W1 [S][C] row-major.
+// One CTA = 4 utterances (weights read from L2 once per 4) x 32 hidden units (4 per warp).
+// grid (ceil(B/4), S/32), block 256, dynamic smem 4*C floats.
 __global__ void __launch_bounds__(256)
-se_mlp_kernel(const float* __restrict__ mean, const float* __restrict__ W1,
-              const float* __restrict__ b1, const float* __restrict__ W2t,
-              const float* __restrict__ b2, int B, int C, int S, float* __restrict__ scale) {
-  extern __shared__ float sm[];
-  float* m = sm;            // [4][C]
-  float* hid = sm + 4 * C;  // [4][S]
+se_hidden_kernel(const float* __restrict__ mean, const float* __restrict__ W1,
+                 const float* __restrict__ b1, int B, int C, int S, float* __restrict__ hid) {
+  extern __shared__ float sm[];  // [4][C]
   const int b0 = blockIdx.x * 4, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = min(4, B - b0);
   for (int i = tid; i < 4 * C; i += 256) {
     const int u = i / C;
-    m[i] = u < nb ? mean[static_cast<size_t>(b0 + u) * C + (i - u * C)] : 0.f;
+    sm[i] = u < nb ? mean[static_cast<size_t>(b0 + u) * C + (i - u * C)] : 0.f;
   }
   __syncthreads();
-  for (int j = warp; j < S; j += 8) {
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = blockIdx.y * 32 + warp * 4 + jj;
+    if (j >= S) break;
     const float4* w = reinterpret_cast<const float4*>(W1 + static_cast<size_t>(j) * C);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+#pragma unroll 8
     for (int i = lane; i < C / 4; i += 32) {
       const float4 wv = __ldg(w + i);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float4 mv = *reinterpret_cast<const float4*>(m + u * C + 4 * i);
+        const float4 mv = *reinterpret_cast<const float4*>(sm + u * C + 4 * i);
         acc[u] += wv.x * mv.x + wv.y * mv.y + wv.z * mv.z + wv.w * mv.w;
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float a = warp_sum(acc[u]);
-      if (lane == 0) hid[u * S + j] = fmaxf(a + b1[j], 0.f);
+      if (lane == 0 && u < nb) hid[static_cast<size_t>(b0 + u) * S + j] = fmaxf(a + b1[j], 0.f);
     }
+  }
+}
+
+// SE excitation, layer 2: scale[b, c] = sigmoid(W2[c, :] . hid[b, :] + b2[c]).   W2t [S][C] (transposed
+// conv2 weight, so consecutive threads read consecutive addresses).
+// grid (ceil(B/4), C/256), block 256.  S <= 128.
+__global__ void __launch_bounds__(256)
+se_scale_kernel(const float* __restrict__ hid, const float* __restrict__ W2t,
+                const float* __restrict__ b2, int B, int C, int S, float* __restrict__ scale) {
+  __shared__ float h[4 * 128];
+  const int b0 = blockIdx.x * 4, tid = threadIdx.x;
+  const int nb = min(4, B - b0);
+  for (int i = tid; i < 4 * S; i += 256) {
+    const int u = i / S;
+    h[i] = u < nb ? hid[static_cast<size_t>(b0 + u) * S + (i - u * S)] : 0.f;
   }
   __syncthreads();
   const int c = blockIdx.y * 256 + tid;
-  if (c < C) {
-    float acc[4];
+  if (c >= C) return;
+  float acc[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = b2[c];
-#pragma unroll 8
-    for (int j = 0; j < S; ++j) {
-      const float wv = __ldg(W2t + static_cast<size_t>(j) * C + c);
+  for (int u = 0; u < 4; ++u) acc[u] = b2[c];
+#pragma unroll 16
+  for (int j = 0; j < S; ++j) {
+    const float wv = __ldg(W2t + static_cast<size_t>(j) * C + c);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] = fmaf(hid[u * S + j], wv, acc[u]);
-    }
-    for (int u = 0; u < nb; ++u) scale[static_cast<size_t>(b0 + u) * C + c] = 1.0f / (1.0f + __expf(-acc[u]));
+    for (int u = 0; u < 4; ++u) acc[u] = fmaf(h[u * S + j], wv, acc[u]);
   }
+  for (int u = 0; u < nb; ++u) scale[static_cast<size_t>(b0 + u) * C + c] = 1.0f / (1.0f + __expf(-acc[u]));
 }
 
 // out[r, c] = w[r, c] * scale[b(r), c] + res[r, c]  over ALL rows (halo rows included, so the

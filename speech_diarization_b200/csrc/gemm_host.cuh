@@ -135,6 +135,7 @@ inline int launch_gemm_chain(const GemmParams* dev_steps, int num_steps, cudaStr
 inline void init_params(GemmParams& P) {
   std::memset(&P, 0, sizeof(P));
   P.acc_slots = 1;
+  P.n_sub = 1;
   P.epi.Tp = 1;
 }
 

@@ -106,6 +106,10 @@ struct alignas(64) GemmParams {
   int n_tile;      // UMMA N and rows of the B box
   int a_row_base;  // added to every A row coordinate (row-block sharding)
   int acc_slots;   // 1, or 3 for EPI_AFF
+  // EPI_POOL on long utterances: a tile's columns (the frames of one utterance) are processed in
+  // n_sub chunks of n_tile rows; B/h rows of chunk s start at n_blk * b_row_stride + s * n_tile.
+  int n_sub;         // >= 1
+  int b_row_stride;  // 0 = n_tile (dense tiling)
   uint32_t idesc;
   KIter kit[MAX_KITERS];
   EpiParams epi;
@@ -334,9 +338,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, int n_blk,
+// running softmax statistics of one channel (one thread), carried across the time chunks of a tile
+struct PoolState {
+  float mx = -INFINITY, se = 0.f, s1 = 0.f, s2 = 0.f;
+};
+
+__device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, int n_blk, int sub,
                                               uint32_t tmem_acc, int quarter, int half, int lane,
-                                              const uint8_t* hbuf, float4* xchg) {
+                                              const uint8_t* hbuf, float4* xchg, PoolState& st) {
   const EpiParams& E = P.epi;
   const int chl = quarter * 32 + lane;  // channel within the tile
   const int ch = m_blk * BM + chl;
@@ -344,30 +353,39 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
   const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
   const bool chv = ch < E.C;
   const float LOG2E = 1.4426950408889634f;
+  const int f0 = sub * P.n_tile - E.H;  // frame index of this chunk's column 0
   // this warp's share of the frames: 16-column chunks  half, half+2, ...
-  // pass 1: max over interior frames
-  float mx = -INFINITY;
+  // pass 1: max over this chunk's interior frames
+  float cm = -INFINITY;
   for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
     uint32_t v[16];
     tmem_ld16(tbase + c0, v);
     tmem_ld_wait();
-    if (c0 >= E.H && c0 + 16 <= E.H + E.T) {
+    if (f0 + c0 >= 0 && f0 + c0 + 16 <= E.T) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+      for (int j = 0; j < 16; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int t = c0 + j - E.H;
-        if (t >= 0 && t < E.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+        const int t = f0 + c0 + j;
+        if (t >= 0 && t < E.T) cm = fmaxf(cm, __uint_as_float(v[j]));
       }
     }
+  }
+  // online softmax: rescale what earlier chunks accumulated to the new running maximum
+  if (cm > st.mx) {
+    const float f = (st.mx == -INFINITY) ? 0.f : ex2_approx((st.mx - cm) * LOG2E);
+    st.se *= f;
+    st.s1 *= f;
+    st.s2 *= f;
+    st.mx = cm;
   }
   // pass 2: softmax-weighted first/second moments about the global mean g
   const float g = chv ? E.gmean[static_cast<size_t>(b) * E.ld_gmean + ch] : 0.f;
   const uint8_t* hchunk = hbuf + (chl >> 6) * (P.n_tile * 128) + (chl & 7) * 2;
   const int c16 = (chl & 63) >> 3;
-  const float mxs = (mx == -INFINITY) ? 0.f : mx * LOG2E;  // a half with no interior frame
-  float se = 0.f, s1 = 0.f, s2 = 0.f;
+  const float mxs = (st.mx == -INFINITY) ? 0.f : st.mx * LOG2E;  // nothing interior seen yet
+  float se = st.se, s1 = st.s1, s2 = st.s2;
   for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
     uint32_t v[16];
     tmem_ld16(tbase + c0, v);
@@ -378,7 +396,7 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
       xv[j] = __half2float(*reinterpret_cast<const __half*>(hchunk + p * 128 + ((c16 ^ (p & 7)) << 4))) - g;
     }
     tmem_ld_wait();
-    if (c0 >= E.H && c0 + 16 <= E.H + E.T) {
+    if (f0 + c0 >= 0 && f0 + c0 + 16 <= E.T) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float e = ex2_approx(fmaf(__uint_as_float(v[j]), LOG2E, -mxs));
@@ -390,7 +408,7 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int t = c0 + j - E.H;
+        const int t = f0 + c0 + j;
         if (t >= 0 && t < E.T) {
           const float e = ex2_approx(fmaf(__uint_as_float(v[j]), LOG2E, -mxs));
           se += e;
@@ -401,13 +419,17 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
       }
     }
   }
-  // combine the two column halves (half 1 -> shared -> half 0)
-  if (half == 1) xchg[chl] = make_float4(mx, se, s1, s2);
+  st.se = se;
+  st.s1 = s1;
+  st.s2 = s2;
+  if (sub + 1 < P.n_sub) return;  // more time chunks of this utterance follow
+  // last chunk: combine the two column halves (half 1 -> shared -> half 0) and finish
+  if (half == 1) xchg[chl] = make_float4(st.mx, se, s1, s2);
   epi_named_barrier();
   if (half == 0) {
     const float4 o = xchg[chl];
-    const float M = fmaxf(mx, o.x);
-    const float fa = (mx == -INFINITY) ? 0.f : ex2_approx((mx - M) * LOG2E);
+    const float M = fmaxf(st.mx, o.x);
+    const float fa = (st.mx == -INFINITY) ? 0.f : ex2_approx((st.mx - M) * LOG2E);
     const float fb = (o.x == -INFINITY) ? 0.f : ex2_approx((o.x - M) * LOG2E);
     se = se * fa + o.y * fb;
     s1 = s1 * fa + o.z * fb;
@@ -427,6 +449,7 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
     }
   }
   epi_named_barrier();  // xchg may be overwritten by the next tile
+  st = PoolState();
 }
 
 // Cosine distance from the three split-f16 partial products:
@@ -558,6 +581,8 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
   const int num_tiles = P.num_m_blocks * P.num_n_blocks;
   const int acc_stages = (P.acc_slots * P.n_tile <= 256) ? 2 : 1;
   const uint32_t tmem_base = c.tmem_base;
+  const int n_sub = P.n_sub < 1 ? 1 : P.n_sub;
+  const int b_row_stride = P.b_row_stride ? P.b_row_stride : P.n_tile;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -569,31 +594,34 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / P.num_n_blocks;
         const int n_blk = tile - m_blk * P.num_n_blocks;
-        if (EPI == EPI_POOL) {
-          // the h tile this tile's epilogue will weight: 128 channels x n_tile rows, two 64-channel boxes
-          mbar_wait(&c.hempty_bar[ps.hs], ps.hphase ^ 1);
-          mbar_arrive_expect_tx(&c.hfull_bar[ps.hs], hbuf_bytes);
-          uint8_t* hb = epi_region + ps.hs * hbuf_bytes;
-          tma_load_2d(hb, &P.tmapH, &c.hfull_bar[ps.hs], m_blk * BM, n_blk * P.n_tile);
-          tma_load_2d(hb + hbuf_bytes / 2, &P.tmapH, &c.hfull_bar[ps.hs], m_blk * BM + BK, n_blk * P.n_tile);
-          if (++ps.hs == 2) { ps.hs = 0; ps.hphase ^= 1; }
-        }
-        for (int k = 0; k < P.num_kiters; ++k) {
-          mbar_wait(&c.empty_bar[ps.stage], ps.phase ^ 1);
-          mbar_arrive_expect_tx(&c.full_bar[ps.stage], tx);
-          uint8_t* sa = smem + ps.stage * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &P.tmapA, &c.full_bar[ps.stage], P.kit[k].a_col,
-                      P.a_row_base + m_blk * BM + P.kit[k].a_row_off);
-          tma_load_2d(sa + Cfg::A_BYTES, &P.tmapB, &c.full_bar[ps.stage], P.kit[k].b_col,
-                      n_blk * P.n_tile);
-          if (++ps.stage == Cfg::STAGES) { ps.stage = 0; ps.phase ^= 1; }
+        for (int sub = 0; sub < n_sub; ++sub) {
+          const int b_row = n_blk * b_row_stride + sub * P.n_tile;
+          if (EPI == EPI_POOL) {
+            // the h tile this chunk's epilogue will weight: 128 channels x n_tile rows, two 64-channel boxes
+            mbar_wait(&c.hempty_bar[ps.hs], ps.hphase ^ 1);
+            mbar_arrive_expect_tx(&c.hfull_bar[ps.hs], hbuf_bytes);
+            uint8_t* hb = epi_region + ps.hs * hbuf_bytes;
+            tma_load_2d(hb, &P.tmapH, &c.hfull_bar[ps.hs], m_blk * BM, b_row);
+            tma_load_2d(hb + hbuf_bytes / 2, &P.tmapH, &c.hfull_bar[ps.hs], m_blk * BM + BK, b_row);
+            if (++ps.hs == 2) { ps.hs = 0; ps.hphase ^= 1; }
+          }
+          for (int k = 0; k < P.num_kiters; ++k) {
+            mbar_wait(&c.empty_bar[ps.stage], ps.phase ^ 1);
+            mbar_arrive_expect_tx(&c.full_bar[ps.stage], tx);
+            uint8_t* sa = smem + ps.stage * Cfg::STAGE_BYTES;
+            tma_load_2d(sa, &P.tmapA, &c.full_bar[ps.stage], P.kit[k].a_col,
+                        P.a_row_base + m_blk * BM + P.kit[k].a_row_off);
+            tma_load_2d(sa + Cfg::A_BYTES, &P.tmapB, &c.full_bar[ps.stage], P.kit[k].b_col, b_row);
+            if (++ps.stage == Cfg::STAGES) { ps.stage = 0; ps.phase ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+      for (int sub = 0; sub < n_sub; ++sub) {
         mbar_wait(&c.tempty_bar[ps.as], ps.aphase ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + ps.as * 256;
@@ -624,7 +652,9 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
     const int half = (warp - 2) >> 2;    // which half of the tile's column chunks it handles
     const int et = threadIdx.x - 64;
     int last_n_blk = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    PoolState pool_state;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    for (int sub = 0; sub < n_sub; ++sub) {
       const int m_blk = tile / P.num_n_blocks;
       const int n_blk = tile - m_blk * P.num_n_blocks;
       if ((EPI == EPI_TDNN || EPI == EPI_ATT) && n_blk != last_n_blk) {
@@ -653,8 +683,8 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       }
       if (EPI == EPI_POOL) {
         mbar_wait(&c.hfull_bar[ps.hs], ps.hphase);
-        epilogue_pool(P, m_blk, n_blk, acc, quarter, half, lane, epi_region + ps.hs * hbuf_bytes,
-                      reinterpret_cast<float4*>(epi_region + 2 * 2 * MAX_BN * 128));
+        epilogue_pool(P, m_blk, n_blk, sub, acc, quarter, half, lane, epi_region + ps.hs * hbuf_bytes,
+                      reinterpret_cast<float4*>(epi_region + 2 * 2 * MAX_BN * 128), pool_state);
         __syncwarp();
         if (lane == 0) mbar_arrive(&c.hempty_bar[ps.hs]);
         if (++ps.hs == 2) { ps.hs = 0; ps.hphase ^= 1; }

@@ -21,7 +21,8 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm())
 
 
-@pytest.mark.parametrize("B,T", [(3, 151), (5, 101), (2, 26), (1, 10), (7, 248)])
+@pytest.mark.parametrize("B,T", [(3, 151), (5, 101), (2, 26), (1, 10), (7, 248),
+                                 (3, 249), (2, 301), (2, 513), (1, 1001)])   # > 248 frames: chunked online-softmax pooling
 def test_trunk_layerwise_and_embedding_parity(oracle_model, encoder, B, T):
     x = eo.synth_features(B, T, seed=B * 100 + T)
     taps = {}
@@ -36,7 +37,7 @@ def test_trunk_layerwise_and_embedding_parity(oracle_model, encoder, B, T):
     assert _rel(got, ref) < 5e-3
 
 
-@pytest.mark.parametrize("n", [24000, 16000, 4000, 8123])
+@pytest.mark.parametrize("n", [24000, 16000, 4000, 8123, 48000, 160000])      # up to 10 s (pyannote chunk length)
 def test_encode_batch_matches_oracle(oracle_model, encoder, n):
     w = synth_wave(6, n, n)
     w[2, n // 2:] = 0.0           # zero-padded member of a variable-length batch
