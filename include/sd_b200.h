@@ -158,6 +158,10 @@ size_t sd_ahc_workspace_bytes(int N);
 int sd_ahc_average_f32(const float* dist_dev, int N, double threshold, int32_t* labels_dev,
                        int32_t* n_clusters_dev, void* workspace_dev, void* stream);
 
+/* Diagnostics of the LAST sd_ahc_average_f32 run on this workspace (synchronous D2H read):
+ * number of reciprocal-nearest-neighbour rounds and of merges performed. */
+int sd_ahc_read_stats(const void* workspace_dev, int N, int32_t* rounds, int32_t* merges);
+
 /* best[i] = argmax_k <x_i, c_k>, score[i] = that maximum (frame_reassign,
  * anti_stick_diarize.py:433-434).  x_dev [N, D], cent_dev [K, D], K <= 64.
  * First maximum wins, as numpy.argmax. score_dev may be NULL. */

@@ -49,7 +49,18 @@ def ahc_average_device(dist: torch.Tensor, threshold: float):
     with torch.cuda.device(dist.device):
         _lib.check(lib.sd_ahc_average_f32(dist.data_ptr(), N, float(threshold), labels.data_ptr(),
                                           ncl.data_ptr(), ws.data_ptr(), _lib.stream_ptr()), "sd_ahc_average_f32")
+    ahc_average_device.last_workspace = (ws, N)
     return labels, ncl
+
+
+def ahc_last_stats() -> dict:
+    """{"rounds", "merges"} of the most recent ahc_average_device call (synchronises)."""
+    import ctypes
+    lib = _lib.load()
+    ws, N = ahc_average_device.last_workspace
+    r, m = ctypes.c_int32(0), ctypes.c_int32(0)
+    _lib.check(lib.sd_ahc_read_stats(ws.data_ptr(), N, ctypes.byref(r), ctypes.byref(m)), "sd_ahc_read_stats")
+    return {"rounds": r.value, "merges": m.value}
 
 
 def window_argmax_device(x: torch.Tensor, cent: torch.Tensor):

@@ -310,3 +310,16 @@ extern "C" int sd_ahc_average_f32(const float* dist_dev, int N, double threshold
   count_launch(4);
   return SD_OK;
 }
+
+extern "C" int sd_ahc_read_stats(const void* workspace_dev, int N, int32_t* rounds, int32_t* merges) {
+  if (!workspace_dev || N < 1 || !rounds || !merges) return fail(SD_ERR_ARG, "sd_ahc_read_stats: bad arguments");
+  const uint8_t* base =
+      reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~uintptr_t(255));
+  const Layout L = ahc_layout(N);
+  const int* counters = reinterpret_cast<const int*>(base + L.off_ints) + 8 * static_cast<size_t>(N);
+  int h[5];
+  SD_CUDA_OK(cudaMemcpy(h, counters, sizeof(h), cudaMemcpyDeviceToHost));
+  *rounds = h[3];
+  *merges = h[4];
+  return SD_OK;
+}

@@ -61,6 +61,9 @@ struct Program {     // launch parameters for one (B, T) shape
   long rows = 0;
   GemmParams block0, tdnn1[3], res[3][7], tdnn2[3], mfa, ctx, att, pool, fc;
   GemmParams* chain_dev = nullptr;  // device copy of [3][9]: tdnn1, 7 x Res2Net, tdnn2 per block
+  cudaGraphExec_t graph = nullptr;  // captured trunk (block0 .. FC) for this shape
+  int graph_launches = 0;
+  int runs = 0;
 };
 
 }  // namespace
@@ -91,6 +94,8 @@ struct SdEcapaPlan {
   // barriers between the steps.  Measured slower than nine stream-ordered launches (0.735 vs 0.623 ms per
   // block at B=512: the per-step pipeline fill/drain costs more than the launch gaps), so it is off.
   bool use_chain = false;
+  bool use_graph = true;   // SD_ECAPA_GRAPH=0 disables CUDA-graph replay of the trunk
+  cudaStream_t cap_stream = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   int forwards_profiled = 0;
@@ -212,6 +217,8 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   }
   if (p->programs.size() > 64) {
     cudaDeviceSynchronize();  // launches that reference the cached descriptors may still be in flight
+    for (auto& kv : p->programs)
+      if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
     p->programs.clear();
     p->last = nullptr;
   }
@@ -298,7 +305,8 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     P.epi.M_rows = B;
     P.epi.N_cols = EMB;
     P.epi.ld_out = EMB;
-    P.epi.bias = p->bfc;   // out pointer is set per call
+    P.epi.bias = p->bfc;
+    P.epi.out = p->emb_tmp;
   }
   // pooling GEMM: rows = channels of asp.conv, columns = the Tp rows of one utterance
   {
@@ -370,7 +378,8 @@ void mark(SdEcapaPlan* p, cudaStream_t st) {
   cudaEventRecord(p->ev_pool[p->ev_used++], st);
 }
 
-int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStream_t st) {
+// The fixed-pointer part of the forward: block0 ... FC, reading p->feats and writing p->emb_tmp.
+int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
   const int B = pr.B, T = pr.T, Tp = pr.Tp;
   const long R = pr.rows;
   mark(p, st);  // end of fbank / start of block0
@@ -417,15 +426,49 @@ int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStr
   mark(p, st);
   SD_TRY(launch_gemm<EPI_POOL>(pr.pool, st));
   mark(p, st);
-  {
-    GemmParams fc = pr.fc;  // the output pointer varies per call
-    fc.epi.out = l2_normalize ? p->emb_tmp : emb;
-    SD_TRY(launch_gemm<EPI_F32>(fc, st));
-    if (l2_normalize) {
-      l2norm_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->emb_tmp, B, EMB, 1e-8f, emb);
-      SD_CUDA_OK(cudaGetLastError());
-      count_launch(1);
-    }
+  SD_TRY(launch_gemm<EPI_F32>(pr.fc, st));
+  return SD_OK;
+}
+
+// Runs the trunk and delivers the embeddings.  After a shape has run once eagerly, its ~45 launches
+// are captured into a CUDA graph and replayed (every pointer inside is a plan-owned buffer, so the
+// graph is static); the caller-dependent ends — fbank reading the caller's audio before it, the
+// L2-norm / copy into the caller's buffer after it — stay ordinary launches.  Replay removes
+// ~0.2 ms of launch gaps per 512-window batch (4.28 -> 4.09 ms measured).
+int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStream_t st) {
+  const int B = pr.B;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  SD_CUDA_OK(cudaStreamIsCapturing(st, &cap));
+  const bool can_graph = p->use_graph && !p->profile && cap == cudaStreamCaptureStatusNone;
+  if (can_graph && pr.graph) {
+    SD_CUDA_OK(cudaGraphLaunch(pr.graph, st));
+    count_launch(pr.graph_launches);
+  } else if (can_graph && pr.runs >= 1) {
+    const long before = launch_counter().load();
+    cudaGraph_t g = nullptr;
+    // capture on a plan-owned stream (the caller's may be the legacy default stream, which cannot
+    // be captured); the instantiated graph is then launched into the caller's stream
+    if (!p->cap_stream) SD_CUDA_OK(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+    SD_CUDA_OK(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = trunk_body(p, pr, p->cap_stream);
+    const cudaError_t ec = cudaStreamEndCapture(p->cap_stream, &g);
+    if (rc != SD_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ec != cudaSuccess) return fail(SD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ec));
+    const cudaError_t ei = cudaGraphInstantiate(&pr.graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) { pr.graph = nullptr; return fail(SD_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ei)); }
+    pr.graph_launches = (int)(launch_counter().load() - before);
+    SD_CUDA_OK(cudaGraphLaunch(pr.graph, st));
+  } else {
+    SD_TRY(trunk_body(p, pr, st));
+  }
+  ++pr.runs;
+  if (l2_normalize) {
+    l2norm_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->emb_tmp, B, EMB, 1e-8f, emb);
+    SD_CUDA_OK(cudaGetLastError());
+    count_launch(1);
+  } else {
+    SD_CUDA_OK(cudaMemcpyAsync(emb, p->emb_tmp, (size_t)B * EMB * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   mark(p, st);  // end of fc
   if (p->profile) ++p->forwards_profiled;
@@ -453,6 +496,7 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   SdEcapaPlan* p = new SdEcapaPlan;
   p->max_batch = max_batch;
   if (const char* e = getenv("SD_ECAPA_CHAIN")) p->use_chain = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_GRAPH")) p->use_graph = atoi(e) != 0;
   p->max_samples = max_samples;
   const int maxT = 1 + max_samples / 160;
   p->max_rows = (long)max_batch * tp_of(maxT);
@@ -564,6 +608,9 @@ extern "C" int sd_ecapa_plan_destroy(SdEcapaPlan* p) {
   if (!p) return SD_OK;
   cudaDeviceSynchronize();
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+  for (auto& kv : p->programs)
+    if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
   for (void* d : p->allocs) cudaFree(d);
   delete p;
   return SD_OK;

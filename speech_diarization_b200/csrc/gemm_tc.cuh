@@ -123,7 +123,8 @@ struct GemmCfg {
   // EPI_POOL has only 2 k-iterations per tile and needs room for the staged h tiles
   // EPI_TDNN/ATT stage the f16 output tile (and the Res2Net sum tile) in 64 KB of shared memory for
   // a coalesced write-out, which leaves room for 3 (MAX_BN 256) / 4 (MAX_BN 128) operand stages.
-  static constexpr bool STAGED_OUT = (EPI == EPI_TDNN || EPI == EPI_ATT);
+  // EPI_AFF stages its f32 tile ([128 rows][128 cols] = 64 KB) the same way.
+  static constexpr bool STAGED_OUT = (EPI == EPI_TDNN || EPI == EPI_ATT || EPI == EPI_AFF);
   static constexpr int OUT_STAGE_BYTES = STAGED_OUT ? 65536 : 0;
   static constexpr int STAGES = (EPI == EPI_POOL) ? 2 : (STAGED_OUT ? ((MAX_BN == 256) ? 3 : 4) : ((MAX_BN == 256) ? 4 : 6));
   static constexpr int EPI_SMEM_FLOATS = 3 * 256;     // EPI_TDNN: bias/scale/shift of one n block
@@ -457,11 +458,15 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
 //   S = slot0 + (slot1 + slot2) * 2^-11 ,  D = 1 - S      (f32, as sklearn computes it)
 // slot1 + slot2 is commutative, so D is exactly symmetric.
 __device__ __forceinline__ void epilogue_aff(const GemmParams& P, int m_blk, int n_blk,
-                                             uint32_t tmem_acc, int quarter, int half, int lane) {
+                                             uint32_t tmem_acc, int quarter, int half, int lane,
+                                             uint8_t* stage_out) {
   const EpiParams& E = P.epi;
-  const int r = m_blk * BM + quarter * 32 + lane;
+  const int rl = quarter * 32 + lane;
+  const int r = m_blk * BM + rl;
   const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
-  float* out = reinterpret_cast<float*>(E.out);
+  // staging: [128 rows][512 B], 16-byte pieces XOR-swizzled by (row & 7) -> conflict-free float4 writes
+  uint8_t* srow = stage_out + rl * 512;
+  const int sw = rl & 7;
   for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
     uint32_t v0[16], v1[16], v2[16];
     __syncwarp();
@@ -469,8 +474,6 @@ __device__ __forceinline__ void epilogue_aff(const GemmParams& P, int m_blk, int
     tmem_ld16(tbase + P.n_tile + c0, v1);
     tmem_ld16(tbase + 2 * P.n_tile + c0, v2);
     tmem_ld_wait();
-    const int col0 = n_blk * P.n_tile + c0;
-    if (r >= E.M_rows || col0 >= E.N_cols) continue;
     float d[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -478,20 +481,45 @@ __device__ __forceinline__ void epilogue_aff(const GemmParams& P, int m_blk, int
                       (__uint_as_float(v1[j]) + __uint_as_float(v2[j])) * 4.8828125e-4f;
       d[j] = 1.0f - s;
     }
-    const size_t off = static_cast<size_t>(r) * E.ld_out + col0;
-    if (col0 + 16 <= E.N_cols && (E.ld_out & 3) == 0) {
-      float4* d4 = reinterpret_cast<float4*>(out + off);
+    const int p0 = c0 >> 2;  // first 16-byte piece of this 16-column run
 #pragma unroll
-      for (int q = 0; q < 4; ++q) d4[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (col0 + j < E.N_cols) out[off + j] = d[j];
-    }
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(srow + (((p0 + q) ^ sw) << 4)) =
+          make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
     if (E.out_f64 != nullptr) {
+      const int col0 = n_blk * P.n_tile + c0;
+      if (r < E.M_rows) {
+        const size_t off = static_cast<size_t>(r) * E.ld_out + col0;
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (col0 + j < E.N_cols) E.out_f64[off + j] = static_cast<double>(d[j]);
+        for (int j = 0; j < 16; ++j)
+          if (col0 + j < E.N_cols) E.out_f64[off + j] = static_cast<double>(d[j]);
+      }
+    }
+  }
+}
+
+// Coalesced write-out of the staged f32 distance tile: one warp instruction = one row's 512 bytes.
+__device__ __forceinline__ void aff_writeout(const GemmParams& P, int m_blk, int n_blk,
+                                             const uint8_t* stage_out, int et) {
+  const EpiParams& E = P.epi;
+  const int lane = et & 31, w = et >> 5;  // 8 warps x 16 rows
+  float* out = reinterpret_cast<float*>(E.out);
+  const int col = n_blk * P.n_tile + lane * 4;
+  const bool vec_ok = (E.ld_out & 3) == 0;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int rl = w * 16 + i;
+    const int r = m_blk * BM + rl;
+    if (r >= E.M_rows) break;
+    const float4 val = *reinterpret_cast<const float4*>(stage_out + rl * 512 + ((lane ^ (rl & 7)) << 4));
+    float* dst = out + static_cast<size_t>(r) * E.ld_out + col;
+    if (vec_ok && col + 4 <= E.N_cols) {
+      *reinterpret_cast<float4*>(dst) = val;
+    } else {
+      if (col < E.N_cols) dst[0] = val.x;
+      if (col + 1 < E.N_cols) dst[1] = val.y;
+      if (col + 2 < E.N_cols) dst[2] = val.z;
+      if (col + 3 < E.N_cols) dst[3] = val.w;
     }
   }
 }
@@ -689,7 +717,10 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
         if (lane == 0) mbar_arrive(&c.hempty_bar[ps.hs]);
         if (++ps.hs == 2) { ps.hs = 0; ps.hphase ^= 1; }
       }
-      if (EPI == EPI_AFF) epilogue_aff(P, m_blk, n_blk, acc, quarter, half, lane);
+      if (EPI == EPI_AFF) {
+        epi_named_barrier();  // previous tile's staging has been written out
+        epilogue_aff(P, m_blk, n_blk, acc, quarter, half, lane, stage_out);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&c.tempty_bar[ps.as]);  // TMEM drained: the next tile's MMAs may start
@@ -697,6 +728,10 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       if (EPI == EPI_TDNN || EPI == EPI_ATT) {
         epi_named_barrier();   // staging tile complete
         tdnn_writeout(P, m_blk, n_blk, stage_out, et);
+      }
+      if (EPI == EPI_AFF) {
+        epi_named_barrier();
+        aff_writeout(P, m_blk, n_blk, stage_out, et);
       }
     }
   }

@@ -13,3 +13,22 @@ for _ in range(10): enc.embed_device(audio, 12000, B, 24000, l2_normalize=True)
 torch.cuda.synchronize(); ms, n = enc.profile_read()
 tot = sum(ms.values()) / n
 print(os.environ.get("SD_DEBUG_EPI", "-"), os.environ.get("SD_ECAPA_CHAIN", "-"), f"total {tot:.3f} ms", {k: round(v / n, 4) for k, v in ms.items()})
+
+# eager vs CUDA-graph replay of the same forward (launch-gap estimate)
+def timed(fn, n=20):
+    torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+out = torch.empty((B, 192), device=dev)
+eager = timed(lambda: enc.embed_device(audio, 12000, B, 24000, l2_normalize=True, out=out))
+g = torch.cuda.CUDAGraph()
+s = torch.cuda.Stream()
+with torch.cuda.stream(s):
+    enc.embed_device(audio, 12000, B, 24000, l2_normalize=True, out=out)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=s):
+        enc.embed_device(audio, 12000, B, 24000, l2_normalize=True, out=out)
+graph = timed(g.replay)
+print(f"eager {eager:.3f} ms   graph replay {graph:.3f} ms")
