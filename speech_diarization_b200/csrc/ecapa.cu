@@ -59,7 +59,7 @@ struct BlockW {
 struct Program {     // launch parameters for one (B, T) shape
   int B = 0, T = 0, Tp = 0;
   long rows = 0;
-  GemmParams block0, tdnn1[3], res[3][7], tdnn2[3], mfa, ctx, att, pool, fc;
+  GemmParams block0, tdnn1[3], res[3][7], resc[3][7], tdnn2[3], mfa, ctx, att, pool, fc;  // resc: EPI_CONV3 form of res
   GemmParams* chain_dev = nullptr;  // device copy of [3][9]: tdnn1, 7 x Res2Net, tdnn2 per block
   cudaGraphExec_t graph = nullptr;  // captured trunk (block0 .. FC) for this shape
   int graph_launches = 0;
@@ -94,6 +94,7 @@ struct SdEcapaPlan {
   // barriers between the steps.  Measured slower than nine stream-ordered launches (0.735 vs 0.623 ms per
   // block at B=512: the per-step pipeline fill/drain costs more than the launch gaps), so it is off.
   bool use_chain = false;
+  bool use_conv3 = true;   // SD_ECAPA_CONV3=0: Res2Net convs through the generic tap-per-k-iteration path
   bool use_graph = true;   // SD_ECAPA_GRAPH=0 disables CUDA-graph replay of the trunk
   cudaStream_t cap_stream = nullptr;
   std::vector<cudaEvent_t> ev_pool;
@@ -256,6 +257,15 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
         G.epi.sum_out = p->s[(i + 1) & 1];
         G.epi.ld_sum = SUB;
       }
+      // the same convolution on the fused-tap / resident-weights operand path (EPI_CONV3)
+      GemmParams& Cv = pr.resc[b][i - 1];
+      Cv = G;
+      SD_TRY(make_tmap_f16(&Cv.tmapA, A, R, a_cols, a_cols, BM + 2 * bw.dil));
+      Cv.num_kiters = SUB / BK;
+      for (int kc = 0; kc < SUB / BK; ++kc) Cv.kit[kc].a_col = a_col0 + kc * BK;
+      Cv.conv_taps = 3;
+      Cv.conv_dil = bw.dil;
+      Cv.conv_cin = SUB;
     }
     SD_TRY(setup_tdnn_gemm(pr.tdnn2[b], p->v, R, C1, C1, bw.tdnn2, C1, C1, 256, C1, 1, 1, 0, pr,
                            p->w, C1, 0, 0));
@@ -396,7 +406,10 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
     } else {
       SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn1[b], st));
       mark(p, st);
-      for (int i = 0; i < 7; ++i) SD_TRY(launch_gemm<EPI_TDNN>(pr.res[b][i], st));
+      for (int i = 0; i < 7; ++i) {
+        if (p->use_conv3) SD_TRY(launch_gemm<EPI_CONV3>(pr.resc[b][i], st));
+        else SD_TRY(launch_gemm<EPI_TDNN>(pr.res[b][i], st));
+      }
       mark(p, st);
       SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn2[b], st));
     }
@@ -497,6 +510,7 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   p->max_batch = max_batch;
   if (const char* e = getenv("SD_ECAPA_CHAIN")) p->use_chain = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_GRAPH")) p->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_CONV3")) p->use_conv3 = atoi(e) != 0;
   p->max_samples = max_samples;
   const int maxT = 1 + max_samples / 160;
   p->max_rows = (long)max_batch * tp_of(maxT);

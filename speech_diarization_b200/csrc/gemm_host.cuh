@@ -108,8 +108,14 @@ inline int launch_gemm(const GemmParams& P, cudaStream_t stream) {
   if (P.n_tile % 16 || P.n_tile < 16 || P.n_tile > 256 || P.num_kiters < 1 ||
       P.num_kiters > MAX_KITERS || P.acc_slots * P.n_tile > TMEM_COLS)
     return SD_ERR_ARG;
-  if (P.n_tile <= 128) return launch_gemm_t<EPI, 128>(P, stream);
-  return launch_gemm_t<EPI, 256>(P, stream);
+  if constexpr (EPI == EPI_CONV3) {
+    if (P.n_tile != 128 || P.conv_taps != 3 || P.num_kiters != 2 || P.conv_dil < 1 || 2 * P.conv_dil > 16)
+      return SD_ERR_ARG;
+    return launch_gemm_t<EPI, 128>(P, stream);
+  } else {
+    if (P.n_tile <= 128) return launch_gemm_t<EPI, 128>(P, stream);
+    return launch_gemm_t<EPI, 256>(P, stream);
+  }
 }
 
 // Cooperative launch of a chain of dependent GEMMs (gemm_chain_kernel); `dev_steps` is a device

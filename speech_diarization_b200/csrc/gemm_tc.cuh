@@ -45,7 +45,14 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 
-enum { EPI_F32 = 0, EPI_TDNN = 1, EPI_POOL = 2, EPI_AFF = 3, EPI_ATT = 4 };
+enum { EPI_F32 = 0, EPI_TDNN = 1, EPI_POOL = 2, EPI_AFF = 3, EPI_ATT = 4, EPI_CONV3 = 5 };
+// EPI_CONV3 = EPI_TDNN's epilogue behind a different operand path for the small dilated k=3 convolutions
+// (Res2Net, 128 -> 128 channels): the tcgen05 unit applies the 128-byte swizzle from ABSOLUTE shared-memory
+// address bits, so an A descriptor may start at any row of a TMA-loaded box (tools/micro/umma_rowoff_test.cu).
+// One (128 + 2d)-row A box per 64-channel chunk therefore serves all three taps (row offsets 0, d, 2d),
+// and the 96 KB of weights stay resident in shared memory for the whole launch: L2 -> SM traffic per tile
+// drops from 192 KB to 34 KB.
+__host__ __device__ constexpr bool epi_is_tdnn(int epi) { return epi == EPI_TDNN || epi == EPI_CONV3; }
 enum {
   EF_REFLECT = 2,   // store interior rows only and mirror them into the halo rows
 };
@@ -110,6 +117,9 @@ struct alignas(64) GemmParams {
   // n_sub chunks of n_tile rows; B/h rows of chunk s start at n_blk * b_row_stride + s * n_tile.
   int n_sub;         // >= 1
   int b_row_stride;  // 0 = n_tile (dense tiling)
+  // EPI_CONV3: taps, dilation (rows), padded input channels per tap in B's K axis; kit[kc].a_col = A column
+  // of 64-channel chunk kc, num_kiters = number of chunks.  tmapA's box has 128 + (taps-1)*dil rows.
+  int conv_taps, conv_dil, conv_cin;
   uint32_t idesc;
   KIter kit[MAX_KITERS];
   EpiParams epi;
@@ -117,22 +127,25 @@ struct alignas(64) GemmParams {
 
 template <int EPI, int MAX_BN>
 struct GemmCfg {
-  static constexpr int A_BYTES = BM * BK * 2;         // 16 KB
+  static constexpr bool CONV = (EPI == EPI_CONV3);
+  static constexpr int A_BYTES = CONV ? 144 * BK * 2 : BM * BK * 2;  // 16 KB; CONV3: up to 128+16 rows = 18 KB
   static constexpr int B_BYTES = MAX_BN * BK * 2;     // 16 / 32 KB
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = CONV ? A_BYTES : A_BYTES + B_BYTES;   // CONV3: B is resident, not staged
+  static constexpr int BRES_BYTES = CONV ? 6 * B_BYTES : 0;                // 3 taps x 2 chunks x [128 x 64] f16
   // EPI_POOL has only 2 k-iterations per tile and needs room for the staged h tiles
   // EPI_TDNN/ATT stage the f16 output tile (and the Res2Net sum tile) in 64 KB of shared memory for
   // a coalesced write-out, which leaves room for 3 (MAX_BN 256) / 4 (MAX_BN 128) operand stages.
   // EPI_AFF stages its f32 tile ([128 rows][128 cols] = 64 KB) the same way.
-  static constexpr bool STAGED_OUT = (EPI == EPI_TDNN || EPI == EPI_ATT || EPI == EPI_AFF);
+  static constexpr bool STAGED_OUT = (epi_is_tdnn(EPI) || EPI == EPI_ATT || EPI == EPI_AFF);
   static constexpr int OUT_STAGE_BYTES = STAGED_OUT ? 65536 : 0;
-  static constexpr int STAGES = (EPI == EPI_POOL) ? 2 : (STAGED_OUT ? ((MAX_BN == 256) ? 3 : 4) : ((MAX_BN == 256) ? 4 : 6));
+  static constexpr int STAGES = CONV ? 3 : (EPI == EPI_POOL) ? 2 : (STAGED_OUT ? ((MAX_BN == 256) ? 3 : 4) : ((MAX_BN == 256) ? 4 : 6));
   static constexpr int EPI_SMEM_FLOATS = 3 * 256;     // EPI_TDNN: bias/scale/shift of one n block
   // EPI_POOL: two buffers of [2 chunks][n_tile rows][128 B] (n_tile <= 256 -> 64 KB each)
   // EPI_POOL additionally needs 2 KB to combine the two column halves of the softmax statistics
   static constexpr int EPI_REGION_BYTES = (EPI == EPI_POOL) ? 2 * 2 * MAX_BN * 128 + 2048 : EPI_SMEM_FLOATS * 4;
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + EPI_REGION_BYTES + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + OUT_STAGE_BYTES + EPI_REGION_BYTES + 256;
+  static_assert(!CONV || MAX_BN == 128, "EPI_CONV3 is built for 128 output channels");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 };
 
@@ -542,6 +555,7 @@ struct PipeState {
   uint32_t aphase = 0;
   int hs = 0;
   uint32_t hphase = 0;
+  uint32_t bphase = 0;  // EPI_CONV3: phase of the resident-weights barrier (one use per GEMM)
 };
 
 template <int EPI, int MAX_BN>
@@ -552,7 +566,7 @@ __device__ __forceinline__ void gemm_setup(uint8_t* smem, GemmCtx& c) {
   // address space and the epilogues' reads compile to LDS rather than generic loads.
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   c.smem = smem;
-  c.epi_region = smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::OUT_STAGE_BYTES;
+  c.epi_region = smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BRES_BYTES + Cfg::OUT_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(c.epi_region + Cfg::EPI_REGION_BYTES);
   c.full_bar = bars;                        // [STAGES]
   c.empty_bar = bars + Cfg::STAGES;         // [STAGES]
@@ -602,7 +616,8 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
   using Cfg = GemmCfg<EPI, MAX_BN>;
   uint8_t* const smem = c.smem;
   uint8_t* const epi_region = c.epi_region;
-  uint8_t* const stage_out = smem + Cfg::STAGES * Cfg::STAGE_BYTES;  // EPI_TDNN/ATT output staging (64 KB)
+  uint8_t* const bres = smem + Cfg::STAGES * Cfg::STAGE_BYTES;        // EPI_CONV3: resident weights (96 KB)
+  uint8_t* const stage_out = bres + Cfg::BRES_BYTES;                  // EPI_TDNN/ATT/AFF output staging (64 KB)
   float* const epi_sp = reinterpret_cast<float*>(epi_region);  // EPI_TDNN: per-column constants
   const uint32_t hbuf_bytes = 2u * static_cast<uint32_t>(P.n_tile) * 128u;  // EPI_POOL: one h tile
   const int warp = c.warp, lane = c.lane;
@@ -619,6 +634,28 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       tma_prefetch_desc(&P.tmapB);
       if (EPI == EPI_POOL) tma_prefetch_desc(&P.tmapH);
       const uint32_t tx = Cfg::A_BYTES + static_cast<uint32_t>(P.n_tile) * BK * 2;
+      if (EPI == EPI_CONV3) {
+        // weights: taps x chunks boxes of [n_tile x 64], loaded once and kept for every tile
+        const uint32_t bbox = static_cast<uint32_t>(P.n_tile) * BK * 2;
+        mbar_arrive_expect_tx(&c.hfull_bar[0], bbox * P.conv_taps * P.num_kiters);
+        for (int kc = 0; kc < P.num_kiters; ++kc)
+          for (int j = 0; j < P.conv_taps; ++j)
+            tma_load_2d(bres + (kc * P.conv_taps + j) * Cfg::B_BYTES, &P.tmapB, &c.hfull_bar[0],
+                        j * P.conv_cin + kc * BK, 0);
+        const int box_rows = BM + (P.conv_taps - 1) * P.conv_dil;
+        const uint32_t txa = static_cast<uint32_t>(box_rows) * BK * 2;
+        const int row_shift = -(P.conv_taps / 2) * P.conv_dil;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int m_blk = tile / P.num_n_blocks;
+          for (int kc = 0; kc < P.num_kiters; ++kc) {
+            mbar_wait(&c.empty_bar[ps.stage], ps.phase ^ 1);
+            mbar_arrive_expect_tx(&c.full_bar[ps.stage], txa);
+            tma_load_2d(smem + ps.stage * Cfg::STAGE_BYTES, &P.tmapA, &c.full_bar[ps.stage], P.kit[kc].a_col,
+                        P.a_row_base + m_blk * BM + row_shift);
+            if (++ps.stage == Cfg::STAGES) { ps.stage = 0; ps.phase ^= 1; }
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / P.num_n_blocks;
         const int n_blk = tile - m_blk * P.num_n_blocks;
@@ -647,7 +684,34 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && EPI == EPI_CONV3) {
+      mbar_wait(&c.hfull_bar[0], ps.bphase);  // resident weights have landed
+      ps.bphase ^= 1;
+      tc_fence_after();
+      const uint32_t bres_addr = smem_u32(bres);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&c.tempty_bar[ps.as], ps.aphase ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + ps.as * 256;
+        for (int kc = 0; kc < P.num_kiters; ++kc) {
+          mbar_wait(&c.full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + ps.stage * Cfg::STAGE_BYTES);
+          for (int j = 0; j < P.conv_taps; ++j) {
+            // tap j = the same box, j*dil rows further down (row pitch 128 B)
+            const uint64_t da = make_smem_desc_sw128(a_addr + j * P.conv_dil * 128);
+            const uint64_t db = make_smem_desc_sw128(bres_addr + (kc * P.conv_taps + j) * Cfg::B_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BK / UMMA_K; ++kk)
+              umma_f16(acc, da + 2 * kk, db + 2 * kk, P.idesc, (kc | j | kk) ? 1u : 0u);
+          }
+          umma_commit(&c.empty_bar[ps.stage]);
+          if (++ps.stage == Cfg::STAGES) { ps.stage = 0; ps.phase ^= 1; }
+        }
+        umma_commit(&c.tfull_bar[ps.as]);
+        if (++ps.as == acc_stages) { ps.as = 0; ps.aphase ^= 1; }
+      }
+    } else if (lane == 0) {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
       for (int sub = 0; sub < n_sub; ++sub) {
         mbar_wait(&c.tempty_bar[ps.as], ps.aphase ^ 1);
@@ -685,7 +749,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
     for (int sub = 0; sub < n_sub; ++sub) {
       const int m_blk = tile / P.num_n_blocks;
       const int n_blk = tile - m_blk * P.num_n_blocks;
-      if ((EPI == EPI_TDNN || EPI == EPI_ATT) && n_blk != last_n_blk) {
+      if ((epi_is_tdnn(EPI) || EPI == EPI_ATT) && n_blk != last_n_blk) {
         // stage this n block's per-column constants (the previous tile's readers all passed the
         // "staging complete" barrier below, so the table may be overwritten)
         last_n_blk = n_blk;
@@ -699,14 +763,14 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
         epi_named_barrier();
       }
       uint4 pre[2][4];
-      if (EPI == EPI_TDNN) tdnn_prefetch(P, m_blk, n_blk, quarter, half, lane, pre);
+      if (epi_is_tdnn(EPI)) tdnn_prefetch(P, m_blk, n_blk, quarter, half, lane, pre);
       mbar_wait(&c.tfull_bar[ps.as], ps.aphase);
       tc_fence_after();
       const uint32_t acc = tmem_base + ps.as * 256;
       if (EPI == EPI_F32) epilogue_f32(P, m_blk, n_blk, acc, quarter, half, lane);
-      if (EPI == EPI_TDNN || EPI == EPI_ATT) {
+      if (epi_is_tdnn(EPI) || EPI == EPI_ATT) {
         epi_named_barrier();  // every thread has finished writing out the previous tile's staging
-        if (EPI == EPI_TDNN) epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre, stage_out);
+        if (epi_is_tdnn(EPI)) epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre, stage_out);
         if (EPI == EPI_ATT) epilogue_tdnn<true>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre, stage_out);
       }
       if (EPI == EPI_POOL) {
@@ -725,7 +789,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       __syncwarp();
       if (lane == 0) mbar_arrive(&c.tempty_bar[ps.as]);  // TMEM drained: the next tile's MMAs may start
       if (++ps.as == acc_stages) { ps.as = 0; ps.aphase ^= 1; }
-      if (EPI == EPI_TDNN || EPI == EPI_ATT) {
+      if (epi_is_tdnn(EPI) || EPI == EPI_ATT) {
         epi_named_barrier();   // staging tile complete
         tdnn_writeout(P, m_blk, n_blk, stage_out, et);
       }
