@@ -45,7 +45,9 @@ struct AhcState {
   int* dirty_list;  // [N]
   int* pair_i;      // [N/2]
   int* pair_j;      // [N/2]
-  int* counters;    // [0] n_dirty(cur) [1] n_dirty(next) [2] n_pairs [3] rounds [4] merges
+  int* act_list;    // [2][N] compact list of live clusters (ping-pong)
+  int* counters;    // [0],[1] n_dirty ping-pong [2] n_pairs [3] rounds [4] merges [5] list length [6] list index
+                    // [7] live clusters [8] staged new list length
   int N;
   double thr;
 };
@@ -81,6 +83,7 @@ __global__ void ahc_init_state_kernel(AhcState S) {
     S.dirty_list[i] = i;
     S.nn_idx[i] = -1;
     S.nn_dist[i] = 1e300;
+    S.act_list[i] = i;
   }
   if (i == 0) {
     S.counters[0] = S.N;
@@ -88,6 +91,10 @@ __global__ void ahc_init_state_kernel(AhcState S) {
     S.counters[2] = 0;
     S.counters[3] = 0;
     S.counters[4] = 0;
+    S.counters[5] = S.N;
+    S.counters[6] = 0;
+    S.counters[7] = S.N;
+    S.counters[8] = 0;
   }
 }
 
@@ -100,6 +107,7 @@ ahc_rounds_kernel(AhcState S) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double red_d[AHC_THREADS / 32];
   __shared__ int red_i[AHC_THREADS / 32];
+  __shared__ int scan_s[AHC_THREADS];
   const int N = S.N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gtid = blockIdx.x * AHC_THREADS + tid;
@@ -107,6 +115,9 @@ ahc_rounds_kernel(AhcState S) {
   int cur = 0;  // which dirty counter is current
 
   for (int round = 0; round < N; ++round) {
+    // the compact list of (mostly) live clusters: late rounds touch a few hundred columns, not N
+    const int* list = S.act_list + static_cast<size_t>(S.counters[6]) * N;
+    const int n_list = S.counters[5];
     // ---- A: nearest neighbour of every dirty row (one CTA per row)
     const int n_dirty = S.counters[cur];
     for (int q = blockIdx.x; q < n_dirty; q += gridDim.x) {
@@ -114,7 +125,8 @@ ahc_rounds_kernel(AhcState S) {
       const double* row = S.D + static_cast<size_t>(r) * N;
       double bd = 1e300;
       int bi = 0x7fffffff;
-      for (int k = tid; k < N; k += AHC_THREADS) {
+      for (int i = tid; i < n_list; i += AHC_THREADS) {
+        const int k = list[i];
         if (k != r && S.active[k]) argmin_combine(bd, bi, row[k], k);
       }
 #pragma unroll
@@ -133,11 +145,10 @@ ahc_rounds_kernel(AhcState S) {
       __syncthreads();
     }
     grid.sync();
-    if (gtid == 0) { S.counters[cur] = 0; S.counters[2] = 0; }
-    grid.sync();
 
     // ---- B: reciprocal nearest neighbours below the threshold
-    for (int r = gtid; r < N; r += gthreads) {
+    for (int i = gtid; i < n_list; i += gthreads) {
+      const int r = list[i];
       if (!S.active[r]) continue;
       const int j = S.nn_idx[r];
       if (j > r && S.nn_dist[r] < S.thr && S.nn_idx[j] == r) {
@@ -152,13 +163,16 @@ ahc_rounds_kernel(AhcState S) {
     const int n_pairs = S.counters[2];
     if (n_pairs == 0) break;
 
-    // ---- C1: rows.  D[i,k] <- (n_i D[i,k] + n_j D[j,k]) / (n_i + n_j) for every k
+    // ---- C1: rows.  D[i,k] <- (n_i D[i,k] + n_j D[j,k]) / (n_i + n_j) for every live k
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const int i = S.pair_i[p], j = S.pair_j[p];
       const double ni = S.size[i], nj = S.size[j], inv = ni + nj;
       double* ri = S.D + static_cast<size_t>(i) * N;
       const double* rj = S.D + static_cast<size_t>(j) * N;
-      for (int k = tid; k < N; k += AHC_THREADS) ri[k] = (ni * ri[k] + nj * rj[k]) / inv;
+      for (int q = tid; q < n_list; q += AHC_THREADS) {
+        const int k = list[q];
+        ri[k] = (ni * ri[k] + nj * rj[k]) / inv;
+      }
     }
     grid.sync();
     // ---- C2: corners between two merged clusters (upper triangle only, i_p < i_q)
@@ -176,7 +190,8 @@ ahc_rounds_kernel(AhcState S) {
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const int i = S.pair_i[p];
       double* ri = S.D + static_cast<size_t>(i) * N;
-      for (int k = tid; k < N; k += AHC_THREADS) {
+      for (int q = tid; q < n_list; q += AHC_THREADS) {
+        const int k = list[q];
         if (k == i || !S.active[k]) continue;
         const int rk = S.role[k];
         if (rk >= 0 && (rk & 1)) continue;  // absorbed this round
@@ -184,10 +199,10 @@ ahc_rounds_kernel(AhcState S) {
         else S.D[static_cast<size_t>(k) * N + i] = ri[k];
       }
     }
-    grid.sync();
-    // ---- D: retire absorbed clusters, mark dirty rows for the next round
+    // ---- D (same phase: touches size/parent/dirty only): retire absorbed clusters, mark dirty rows
     const int nxt = cur ^ 1;
-    for (int r = gtid; r < N; r += gthreads) {
+    for (int q = gtid; q < n_list; q += gthreads) {
+      const int r = list[q];
       if (!S.active[r]) continue;
       const int rr = S.role[r];
       if (rr >= 0 && (rr & 1)) continue;  // absorbed: handled by its partner below
@@ -203,14 +218,51 @@ ahc_rounds_kernel(AhcState S) {
       }
       if (dirty) S.dirty_list[atomicAdd(&S.counters[nxt], 1)] = r;
     }
+    // ---- compaction of the live list (block 0, only when a quarter of it is dead)
+    const int n_alive_after = S.counters[7] - n_pairs;
+    const bool rebuild = (n_list - n_alive_after) * 4 > n_list;
+    if (rebuild && blockIdx.x == 0) {
+      int* out = S.act_list + static_cast<size_t>(S.counters[6] ^ 1) * N;
+      const int chunk = (n_list + AHC_THREADS - 1) / AHC_THREADS;
+      const int lo = tid * chunk, hi = min(n_list, lo + chunk);
+      int cnt = 0;
+      for (int q = lo; q < hi; ++q) {
+        const int k = list[q];
+        const int rk = S.role[k];
+        cnt += (S.active[k] && !(rk >= 0 && (rk & 1))) ? 1 : 0;
+      }
+      scan_s[tid] = cnt;
+      __syncthreads();
+      for (int o = 1; o < AHC_THREADS; o <<= 1) {
+        const int v = tid >= o ? scan_s[tid - o] : 0;
+        __syncthreads();
+        scan_s[tid] += v;
+        __syncthreads();
+      }
+      int w = scan_s[tid] - cnt;
+      for (int q = lo; q < hi; ++q) {
+        const int k = list[q];
+        const int rk = S.role[k];
+        if (S.active[k] && !(rk >= 0 && (rk & 1))) out[w++] = k;
+      }
+      if (tid == AHC_THREADS - 1) S.counters[8] = scan_s[tid];  // new length, committed in the clean-up phase
+    }
     grid.sync();
+    // ---- clean-up
     for (int p = gtid; p < n_pairs; p += gthreads) {
       const int i = S.pair_i[p], j = S.pair_j[p];
       S.active[j] = 0;
       S.role[i] = -1;
       S.role[j] = -1;
     }
-    if (gtid == 0) { S.counters[3] = round + 1; S.counters[4] += n_pairs; }
+    if (gtid == 0) {
+      S.counters[cur] = 0;  // consumed dirty counter becomes next round's target
+      S.counters[2] = 0;
+      S.counters[3] = round + 1;
+      S.counters[4] += n_pairs;
+      S.counters[7] = n_alive_after;
+      if (rebuild) { S.counters[5] = S.counters[8]; S.counters[6] ^= 1; }
+    }
     cur = nxt;
     grid.sync();
   }
@@ -259,7 +311,7 @@ Layout ahc_layout(int N) {
   L.off_nn_dist = o;
   o += static_cast<size_t>(N) * 8;
   L.off_ints = o;
-  o += (static_cast<size_t>(N) * 8 + 64) * 4;  // 7 int arrays + scratch + counters
+  o += (static_cast<size_t>(N) * 10 + 64) * 4;  // 7 int arrays + scratch + counters + 2 live lists
   L.total = o + 256;
   return L;
 }
@@ -288,9 +340,10 @@ extern "C" int sd_ahc_average_f32(const float* dist_dev, int N, double threshold
   S.role = ip + 4 * static_cast<size_t>(N);
   S.dirty_list = ip + 5 * static_cast<size_t>(N);
   S.pair_i = ip + 6 * static_cast<size_t>(N);
-  S.pair_j = S.pair_i + (N / 2 + 1);
+  S.pair_j = S.pair_i + (N + 1) / 2;  // at most floor(N/2) pairs per round
   int* scratch = ip + 7 * static_cast<size_t>(N);
   S.counters = ip + 8 * static_cast<size_t>(N);
+  S.act_list = ip + 8 * static_cast<size_t>(N) + 64;
 
   const int nb = (N + 31) / 32;
   ahc_init_matrix_kernel<<<dim3(nb, nb), 256, 0, st>>>(dist_dev, N, S.D);
