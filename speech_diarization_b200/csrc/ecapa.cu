@@ -42,6 +42,7 @@ constexpr int SUB = 128;   // Res2Net sub-band width (C1 / scale 8)
 constexpr int EMB = 192;
 constexpr int FEAT_P = 128; // 80 mel channels padded to two 64-element K chunks
 constexpr int HALO = 4;
+constexpr int KSPLIT = 8;   // split-K factor of the two per-utterance dense layers (context bias, FC)
 
 struct TdnnW {       // one TDNNBlock: conv weight (f16, [Cout, taps*CinP]) + folded epilogue constants
   __half* W = nullptr;
@@ -84,7 +85,7 @@ struct SdEcapaPlan {
   __half *feats = nullptr, *x0 = nullptr, *cat = nullptr, *u = nullptr, *v = nullptr, *w = nullptr;
   __half *s[2] = {nullptr, nullptr}, *h = nullptr, *attn = nullptr;
   float *raw = nullptr, *se_mean = nullptr, *se_hid = nullptr, *se_scale = nullptr, *stats = nullptr;
-  float *uttbias = nullptr, *pooled = nullptr, *emb_tmp = nullptr;
+  float *uttbias = nullptr, *pooled = nullptr, *emb_tmp = nullptr, *ctx_part = nullptr;
   __half *stats_h = nullptr, *pooled_h = nullptr;
   std::map<std::pair<int, int>, Program> programs;
   Program* last = nullptr;
@@ -293,8 +294,10 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     }
     P.epi.M_rows = B;
     P.epi.N_cols = ATT;
-    P.epi.out = p->uttbias;
+    P.epi.out = p->ctx_part;
     P.epi.ld_out = ATT;
+    P.k_splits = KSPLIT;   // 96 k-iterations over 8 CTAs per output tile
+    P.split_stride = (long)B * ATT;
   }
   // final FC (asp_bn folded): emb[b, :] = Wfc . pooled[b] + bfc
   {
@@ -316,7 +319,9 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     P.epi.N_cols = EMB;
     P.epi.ld_out = EMB;
     P.epi.bias = p->bfc;
-    P.epi.out = p->emb_tmp;
+    P.epi.out = p->emb_tmp;   // [KSPLIT][B][EMB] partial sums, reduced by fc_finish_kernel
+    P.k_splits = KSPLIT;
+    P.split_stride = (long)B * EMB;
   }
   // pooling GEMM: rows = channels of asp.conv, columns = the Tp rows of one utterance
   {
@@ -434,6 +439,9 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
   count_launch(1);
   // context bias: W_mean . mean + W_std . std  (the 2/3 of asp.tdnn that is constant over time)
   SD_TRY(launch_gemm<EPI_F32>(pr.ctx, st));
+  sum_splits_kernel<<<(B * ATT + 255) / 256, 256, 0, st>>>(p->ctx_part, KSPLIT, (long)B * ATT, (long)B * ATT, p->uttbias);
+  SD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
   mark(p, st);
   SD_TRY(launch_gemm<EPI_ATT>(pr.att, st));
   mark(p, st);
@@ -476,13 +484,9 @@ int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStr
     SD_TRY(trunk_body(p, pr, st));
   }
   ++pr.runs;
-  if (l2_normalize) {
-    l2norm_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->emb_tmp, B, EMB, 1e-8f, emb);
-    SD_CUDA_OK(cudaGetLastError());
-    count_launch(1);
-  } else {
-    SD_CUDA_OK(cudaMemcpyAsync(emb, p->emb_tmp, (size_t)B * EMB * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  }
+  fc_finish_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->emb_tmp, KSPLIT, (long)B * EMB, B, EMB, l2_normalize, 1e-8f, emb);
+  SD_CUDA_OK(cudaGetLastError());
+  count_launch(1);
   mark(p, st);  // end of fc
   if (p->profile) ++p->forwards_profiled;
   p->last = &pr;
@@ -602,7 +606,8 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
     SD_TRY(dev_alloc(p, (void**)&p->stats, MB * 2 * C3 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->uttbias, MB * ATT * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->pooled, MB * 2 * C3 * 4, true));
-    SD_TRY(dev_alloc(p, (void**)&p->emb_tmp, MB * EMB * 4, true));
+    SD_TRY(dev_alloc(p, (void**)&p->emb_tmp, MB * EMB * 4 * KSPLIT, true));
+    SD_TRY(dev_alloc(p, (void**)&p->ctx_part, MB * ATT * 4 * KSPLIT, true));
     SD_TRY(dev_alloc(p, (void**)&p->stats_h, MB * 2 * C3 * 2, true));
     SD_TRY(dev_alloc(p, (void**)&p->pooled_h, MB * 2 * C3 * 2, true));
     SD_CUDA_OK(cudaDeviceSynchronize());

@@ -244,6 +244,45 @@ l2norm_rows_kernel(const float* __restrict__ x, int N, int D, float eps, float* 
   for (int i = lane; i < D; i += 32) out[static_cast<size_t>(row) * D + i] = p[i] * inv;
 }
 
+// out[i] = sum_s partial[s * stride + i]  (split-K partial sums, fixed order)
+__global__ void __launch_bounds__(256)
+sum_splits_kernel(const float* __restrict__ partial, int n_splits, long stride, long count,
+                  float* __restrict__ out) {
+  const long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= count) return;
+  float acc = 0.f;
+  for (int s = 0; s < n_splits; ++s) acc += partial[s * stride + i];
+  out[i] = acc;
+}
+
+// Final step of the embedding: e = sum of the FC's split-K partials (bias already inside split 0),
+// optionally e / (||e|| + eps).  One warp per utterance.
+__global__ void __launch_bounds__(256)
+fc_finish_kernel(const float* __restrict__ partial, int n_splits, long stride, int B, int D,
+                 int l2_normalize, float eps, float* __restrict__ emb) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float v[8];  // D <= 256
+  float ss = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = lane + 32 * q;
+    float acc = 0.f;
+    if (c < D)
+      for (int s = 0; s < n_splits; ++s) acc += partial[s * stride + static_cast<long>(row) * D + c];
+    v[q] = acc;
+    ss = fmaf(acc, acc, ss);
+  }
+  float inv = 1.f;
+  if (l2_normalize) inv = 1.0f / (sqrtf(warp_sum(ss)) + eps);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = lane + 32 * q;
+    if (c < D) emb[static_cast<long>(row) * D + c] = v[q] * inv;
+  }
+}
+
 // test hook: interior frames of a padded f16 tensor -> f32 [B, T, C]
 __global__ void __launch_bounds__(256)
 fetch_interior_kernel(const __half* __restrict__ x, int ld, int col_off, int Tp, int T, int H,

@@ -36,17 +36,18 @@ constexpr int NBIN = 201;
 constexpr int NMEL = 80;
 constexpr int MEL_MAXLEN = 16;
 constexpr int FR_PER_CTA = 32;
-constexpr int ZSTRIDE = 201;  // float2 per frame (200 used; odd stride spreads banks)
+constexpr int ZSTRIDE = 200;  // float2 per frame: 400 words = 16 mod 32, so the two frames of a half-warp in the
+                              // 25-point stage (lane stride 25 float2) hit disjoint bank pairs
 constexpr int PSTRIDE = 204;  // floats per frame of power
 
 struct FbankTables {
   float window[NFFT];
-  float2 tw200[200];  // W_200^(n2*k1) at [n2*8 + k1]
+  float2 tw200[200];  // W_200^(n2*k1) at [k1*25 + n2] (consecutive lanes = consecutive n2)
   float2 tw400[NBIN]; // W_400^k
   float2 tw25[25];    // W_25^j
   int mel_start[NMEL];
   int mel_len[NMEL];
-  float mel_w[NMEL * MEL_MAXLEN];
+  float mel_w[MEL_MAXLEN * NMEL];  // [tap j][mel m]: consecutive lanes (mels) read consecutive words
 };
 
 struct FbankSmem {
@@ -120,8 +121,9 @@ fbank_frames_kernel(const float* __restrict__ wav, long wav_stride, int n_sample
 #pragma unroll
       for (int n1 = 0; n1 < 8; ++n1) {
         const int n = 2 * (25 * n1 + n2);
-        a[n1].x = S.tab.window[n] * load_sample<VARIANT>(w, base + n, n_samples);
-        a[n1].y = S.tab.window[n + 1] * load_sample<VARIANT>(w, base + n + 1, n_samples);
+        const float2 wn = *reinterpret_cast<const float2*>(&S.tab.window[n]);
+        a[n1].x = wn.x * load_sample<VARIANT>(w, base + n, n_samples);
+        a[n1].y = wn.y * load_sample<VARIANT>(w, base + n + 1, n_samples);
       }
     } else {
 #pragma unroll
@@ -141,7 +143,7 @@ fbank_frames_kernel(const float* __restrict__ wav, long wav_stride, int n_sample
     X[3] = cadd(c3, w3c7); X[7] = csub(c3, w3c7);
     float2* zf = S.z + fl * ZSTRIDE;
 #pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) zf[k1 * 25 + n2] = cmul(X[k1], S.tab.tw200[n2 * 8 + k1]);
+    for (int k1 = 0; k1 < 8; ++k1) zf[k1 * 25 + n2] = cmul(X[k1], S.tab.tw200[k1 * 25 + n2]);
   }
   __syncwarp();
 
@@ -195,10 +197,10 @@ fbank_frames_kernel(const float* __restrict__ wav, long wav_stride, int n_sample
     const int f = f0 + fl;
     if (f >= T) break;
     const float* p = S.pw + fl * PSTRIDE + S.tab.mel_start[m];
-    const float* mw = S.tab.mel_w + m * MEL_MAXLEN;
+    const float* mw = S.tab.mel_w + m;
     const int len = S.tab.mel_len[m];
     float acc = 0.f;
-    for (int j = 0; j < len; ++j) acc = fmaf(p[j], mw[j], acc);
+    for (int j = 0; j < len; ++j) acc = fmaf(p[j], mw[j * NMEL], acc);
     float v;
     if (VARIANT == 0) v = logf(acc + 1e-6f);
     else v = 10.0f * log10f(fmaxf(acc, 1e-10f));
@@ -278,7 +280,7 @@ static void build_tables(int variant, FbankTables& t) {
   for (int n2 = 0; n2 < 25; ++n2)
     for (int k1 = 0; k1 < 8; ++k1) {
       const double a = -2.0 * PI * (n2 * k1) / 200.0;
-      t.tw200[n2 * 8 + k1] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+      t.tw200[k1 * 25 + n2] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
     }
   for (int k = 0; k < NBIN; ++k) {
     const double a = -2.0 * PI * k / 400.0;
@@ -329,7 +331,7 @@ static void build_tables(int variant, FbankTables& t) {
     t.mel_start[m] = lo < 0 ? 0 : lo;
     t.mel_len[m] = len;
     for (int j = 0; j < MEL_MAXLEN; ++j)
-      t.mel_w[m * MEL_MAXLEN + j] = j < len ? static_cast<float>(fb[(lo + j) * NMEL + m]) : 0.f;
+      t.mel_w[j * NMEL + m] = j < len ? static_cast<float>(fb[(lo + j) * NMEL + m]) : 0.f;
   }
 }
 

@@ -88,7 +88,7 @@ inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
       return SD_ERR_CUDA;
     attr_set = true;
   }
-  const int tiles = P.num_m_blocks * P.num_n_blocks;
+  const int tiles = P.num_m_blocks * P.num_n_blocks * (P.k_splits > 1 ? P.k_splits : 1);
   if (tiles <= 0) return SD_OK;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_tc_kernel<EPI, MAX_BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(P);
@@ -142,6 +142,7 @@ inline void init_params(GemmParams& P) {
   std::memset(&P, 0, sizeof(P));
   P.acc_slots = 1;
   P.n_sub = 1;
+  P.k_splits = 1;
   P.epi.Tp = 1;
 }
 

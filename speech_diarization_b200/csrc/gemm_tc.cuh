@@ -120,6 +120,12 @@ struct alignas(64) GemmParams {
   // EPI_CONV3: taps, dilation (rows), padded input channels per tap in B's K axis; kit[kc].a_col = A column
   // of 64-channel chunk kc, num_kiters = number of chunks.  tmapA's box has 128 + (taps-1)*dil rows.
   int conv_taps, conv_dil, conv_cin;
+  // split-K (EPI_F32 only): the k-iterations are divided among k_splits CTAs per output tile; split s
+  // stores its partial sums at out + s * split_stride (elements) and a tiny follow-up kernel adds them in a
+  // fixed order (deterministic, unlike atomics).  For the skinny per-utterance dense layers (M = batch,
+  // K = 6144) that would otherwise occupy 4 SMs.
+  int k_splits;  // >= 1
+  long split_stride;
   uint32_t idesc;
   KIter kit[MAX_KITERS];
   EpiParams epi;
@@ -155,7 +161,7 @@ __device__ __forceinline__ void epi_named_barrier() {
 }
 
 // raw f32
-__device__ __forceinline__ void epilogue_f32(const GemmParams& P, int m_blk, int n_blk,
+__device__ __forceinline__ void epilogue_f32(const GemmParams& P, int m_blk, int n_blk, int ksplit,
                                              uint32_t tmem_acc, int quarter, int half, int lane) {
   const EpiParams& E = P.epi;
   const int r = m_blk * BM + quarter * 32 + lane;
@@ -170,7 +176,10 @@ __device__ __forceinline__ void epilogue_f32(const GemmParams& P, int m_blk, int
       float* dst = out + static_cast<size_t>(r) * E.ld_out + E.out_col_off + col0;
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (col0 + j < E.N_cols) dst[j] = __uint_as_float(v[j]) + (E.bias ? __ldg(E.bias + col0 + j) : 0.f);
+        if (col0 + j < E.N_cols) {
+          dst[j + ksplit * P.split_stride] =
+              __uint_as_float(v[j]) + ((E.bias && ksplit == 0) ? __ldg(E.bias + col0 + j) : 0.f);
+        }
     }
   }
 }
@@ -621,7 +630,9 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
   float* const epi_sp = reinterpret_cast<float*>(epi_region);  // EPI_TDNN: per-column constants
   const uint32_t hbuf_bytes = 2u * static_cast<uint32_t>(P.n_tile) * 128u;  // EPI_POOL: one h tile
   const int warp = c.warp, lane = c.lane;
-  const int num_tiles = P.num_m_blocks * P.num_n_blocks;
+  const int k_splits = P.k_splits < 1 ? 1 : P.k_splits;
+  const int k_per = (P.num_kiters + k_splits - 1) / k_splits;
+  const int num_tiles = P.num_m_blocks * P.num_n_blocks * k_splits;  // split index fastest
   const int acc_stages = (P.acc_slots * P.n_tile <= 256) ? 2 : 1;
   const uint32_t tmem_base = c.tmem_base;
   const int n_sub = P.n_sub < 1 ? 1 : P.n_sub;
@@ -657,8 +668,10 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
         }
       } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / P.num_n_blocks;
-        const int n_blk = tile - m_blk * P.num_n_blocks;
+        const int ot = tile / k_splits, ks = tile - ot * k_splits;
+        const int m_blk = ot / P.num_n_blocks;
+        const int n_blk = ot - m_blk * P.num_n_blocks;
+        const int k_begin = ks * k_per, k_end = min(P.num_kiters, k_begin + k_per);
         for (int sub = 0; sub < n_sub; ++sub) {
           const int b_row = n_blk * b_row_stride + sub * P.n_tile;
           if (EPI == EPI_POOL) {
@@ -670,7 +683,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
             tma_load_2d(hb + hbuf_bytes / 2, &P.tmapH, &c.hfull_bar[ps.hs], m_blk * BM + BK, b_row);
             if (++ps.hs == 2) { ps.hs = 0; ps.hphase ^= 1; }
           }
-          for (int k = 0; k < P.num_kiters; ++k) {
+          for (int k = k_begin; k < k_end; ++k) {
             mbar_wait(&c.empty_bar[ps.stage], ps.phase ^ 1);
             mbar_arrive_expect_tx(&c.full_bar[ps.stage], tx);
             uint8_t* sa = smem + ps.stage * Cfg::STAGE_BYTES;
@@ -714,10 +727,12 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
     } else if (lane == 0) {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
       for (int sub = 0; sub < n_sub; ++sub) {
+        const int ks = tile % k_splits;
+        const int k_begin = ks * k_per, k_end = min(P.num_kiters, k_begin + k_per);
         mbar_wait(&c.tempty_bar[ps.as], ps.aphase ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + ps.as * 256;
-        for (int k = 0; k < P.num_kiters; ++k) {
+        for (int k = k_begin; k < k_end; ++k) {
           mbar_wait(&c.full_bar[ps.stage], ps.phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + ps.stage * Cfg::STAGE_BYTES);
@@ -729,7 +744,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
           for (int kk = 0; kk < BK / UMMA_K; ++kk) {
             // advance 16 elements = 32 bytes inside the swizzle span: +2 in the (addr>>4) field
             umma_f16(d_addr, da + 2 * kk, db + 2 * kk, P.idesc,
-                     (P.kit[k].accum | kk) ? 1u : 0u);
+                     ((k > k_begin && P.kit[k].accum) || kk) ? 1u : 0u);
           }
           umma_commit(&c.empty_bar[ps.stage]);  // frees the smem slot once these MMAs retire
           if (++ps.stage == Cfg::STAGES) { ps.stage = 0; ps.phase ^= 1; }
@@ -747,8 +762,9 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
     PoolState pool_state;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
     for (int sub = 0; sub < n_sub; ++sub) {
-      const int m_blk = tile / P.num_n_blocks;
-      const int n_blk = tile - m_blk * P.num_n_blocks;
+      const int ot = tile / k_splits, ksplit = tile - ot * k_splits;
+      const int m_blk = ot / P.num_n_blocks;
+      const int n_blk = ot - m_blk * P.num_n_blocks;
       if ((epi_is_tdnn(EPI) || EPI == EPI_ATT) && n_blk != last_n_blk) {
         // stage this n block's per-column constants (the previous tile's readers all passed the
         // "staging complete" barrier below, so the table may be overwritten)
@@ -767,7 +783,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       mbar_wait(&c.tfull_bar[ps.as], ps.aphase);
       tc_fence_after();
       const uint32_t acc = tmem_base + ps.as * 256;
-      if (EPI == EPI_F32) epilogue_f32(P, m_blk, n_blk, acc, quarter, half, lane);
+      if (EPI == EPI_F32) epilogue_f32(P, m_blk, n_blk, ksplit, acc, quarter, half, lane);
       if (epi_is_tdnn(EPI) || EPI == EPI_ATT) {
         epi_named_barrier();  // every thread has finished writing out the previous tile's staging
         if (epi_is_tdnn(EPI)) epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre, stage_out);
