@@ -95,6 +95,9 @@ struct SdEcapaPlan {
   // barriers between the steps.  Measured slower than nine stream-ordered launches (0.735 vs 0.623 ms per
   // block at B=512: the per-step pipeline fill/drain costs more than the launch gaps), so it is off.
   bool use_chain = false;
+  // SD_ECAPA_MC=1: 256-wide GEMMs on 2-CTA clusters with the weight tile multicast.  Correct, but only ~3% faster
+  // on the MFA layer and neutral elsewhere (the GEMMs are bound by per-SM operand ingest, not by L2), so off.
+  bool use_mc = false;
   bool use_conv3 = true;   // SD_ECAPA_CONV3=0: Res2Net convs through the generic tap-per-k-iteration path
   bool use_graph = true;   // SD_ECAPA_GRAPH=0 disables CUDA-graph replay of the trunk
   cudaStream_t cap_stream = nullptr;
@@ -175,10 +178,11 @@ inline int tp_of(int T) { return ((T + 2 * HALO + 15) / 16) * 16; }
 int setup_tdnn_gemm(GemmParams& P, const __half* A, long rows, int a_cols, int ld_a,
                     const TdnnW& W, int cout, int k_total, int n_tile, int cin_p, int taps,
                     int dil, int a_col0, const Program& pr, void* out, int ld_out, int out_col0,
-                    int flags) {
+                    int flags, bool mc = false) {
   init_params(P);
   SD_TRY(make_tmap_f16(&P.tmapA, A, rows, a_cols, ld_a, BM));
-  SD_TRY(make_tmap_f16(&P.tmapB, W.W, cout, k_total, k_total, n_tile));
+  // mc: launched on 2-CTA clusters, each CTA fetches (and multicasts) half of the B tile
+  SD_TRY(make_tmap_f16(&P.tmapB, W.W, cout, k_total, k_total, mc ? n_tile / 2 : n_tile));
   P.num_m_blocks = (int)((rows + BM - 1) / BM);
   P.num_n_blocks = cout / n_tile;
   P.n_tile = n_tile;
@@ -232,14 +236,14 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   const long R = pr.rows;
   // block0: k = 5 over the 128-padded mel channels
   SD_TRY(setup_tdnn_gemm(pr.block0, p->feats, R, FEAT_P, FEAT_P, p->w0, C1, 5 * FEAT_P, 256, FEAT_P,
-                         5, 1, 0, pr, p->x0, C1, 0, EF_REFLECT));
+                         5, 1, 0, pr, p->x0, C1, 0, EF_REFLECT, p->use_mc));
   for (int b = 0; b < 3; ++b) {
     const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
     const int ld_in = b == 0 ? C1 : C3;
     const BlockW& bw = p->blk[b];
     // tdnn1: 1x1, also copies sub-band 0 into v (Res2Net passes it through)
     SD_TRY(setup_tdnn_gemm(pr.tdnn1[b], in, R, C1, ld_in, bw.tdnn1, C1, C1, 256, C1, 1, 1, 0, pr,
-                           p->u, C1, 0, 0));
+                           p->u, C1, 0, 0, p->use_mc));
     pr.tdnn1[b].epi.out2 = p->v;
     pr.tdnn1[b].epi.ld_out2 = C1;
     pr.tdnn1[b].epi.out2_cols = SUB;
@@ -269,10 +273,10 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
       Cv.conv_cin = SUB;
     }
     SD_TRY(setup_tdnn_gemm(pr.tdnn2[b], p->v, R, C1, C1, bw.tdnn2, C1, C1, 256, C1, 1, 1, 0, pr,
-                           p->w, C1, 0, 0));
+                           p->w, C1, 0, 0, p->use_mc));
   }
   SD_TRY(setup_tdnn_gemm(pr.mfa, p->cat, R, C3, C3, p->wmfa, C3, C3, 256, C3, 1, 1, 0, pr, p->h, C3,
-                         0, 0));
+                         0, 0, p->use_mc));
   SD_TRY(setup_tdnn_gemm(pr.att, p->h, R, C3, C3, p->watt, ATT, C3, 128, C3, 1, 1, 0, pr, p->attn,
                          ATT, 0, 0));
   pr.att.epi.utt_bias = p->uttbias;
@@ -393,12 +397,18 @@ void mark(SdEcapaPlan* p, cudaStream_t st) {
   cudaEventRecord(p->ev_pool[p->ev_used++], st);
 }
 
+// the 256-wide TDNN GEMMs (block0, tdnn1/2, MFA): 2-CTA multicast variant unless disabled
+int launch_big(SdEcapaPlan* p, const GemmParams& P, cudaStream_t st) {
+  if (p->use_mc) return launch_gemm_mc_t<EPI_TDNN, 256>(P, st);
+  return launch_gemm<EPI_TDNN>(P, st);
+}
+
 // The fixed-pointer part of the forward: block0 ... FC, reading p->feats and writing p->emb_tmp.
 int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
   const int B = pr.B, T = pr.T, Tp = pr.Tp;
   const long R = pr.rows;
   mark(p, st);  // end of fbank / start of block0
-  SD_TRY(launch_gemm<EPI_TDNN>(pr.block0, st));
+  SD_TRY(launch_big(p, pr.block0, st));
   for (int b = 0; b < 3; ++b) {
     const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
     const int ld_in = b == 0 ? C1 : C3;
@@ -409,14 +419,14 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
       mark(p, st);
       mark(p, st);
     } else {
-      SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn1[b], st));
+      SD_TRY(launch_big(p, pr.tdnn1[b], st));
       mark(p, st);
       for (int i = 0; i < 7; ++i) {
         if (p->use_conv3) SD_TRY(launch_gemm<EPI_CONV3>(pr.resc[b][i], st));
         else SD_TRY(launch_gemm<EPI_TDNN>(pr.res[b][i], st));
       }
       mark(p, st);
-      SD_TRY(launch_gemm<EPI_TDNN>(pr.tdnn2[b], st));
+      SD_TRY(launch_big(p, pr.tdnn2[b], st));
     }
     mark(p, st);
     time_mean_kernel<<<dim3(C1 / 256, B), 128, 0, st>>>(p->w, C1, Tp, T, HALO, C1, p->se_mean);
@@ -432,7 +442,7 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
     count_launch(4);
   }
   mark(p, st);
-  SD_TRY(launch_gemm<EPI_TDNN>(pr.mfa, st));
+  SD_TRY(launch_big(p, pr.mfa, st));
   mark(p, st);
   time_mean_std_kernel<<<dim3(C3 / 256, B), 128, 0, st>>>(p->h, C3, Tp, T, HALO, C3, p->stats, p->stats_h);
   SD_CUDA_OK(cudaGetLastError());
@@ -515,6 +525,8 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   if (const char* e = getenv("SD_ECAPA_CHAIN")) p->use_chain = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_GRAPH")) p->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_CONV3")) p->use_conv3 = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_MC")) p->use_mc = atoi(e) != 0;
+  if (p->use_chain) p->use_mc = false;  // the cooperative chain uses the plain kernels
   p->max_samples = max_samples;
   const int maxT = 1 + max_samples / 160;
   p->max_rows = (long)max_batch * tp_of(maxT);

@@ -102,6 +102,42 @@ inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
   return SD_OK;
 }
 
+// 2-CTA-cluster launch with the B tile multicast (gemm_tc_mc_kernel).  tmapB's box must hold n_tile / 2 rows.
+template <int EPI, int MAX_BN>
+inline int launch_gemm_mc_t(const GemmParams& P, cudaStream_t stream) {
+  using Cfg = GemmCfg<EPI, MAX_BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_mc_kernel<EPI, MAX_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::SMEM_BYTES) != cudaSuccess)
+      return SD_ERR_CUDA;
+    attr_set = true;
+  }
+  const int units = ((P.num_m_blocks + 1) / 2) * P.num_n_blocks;
+  if (units <= 0) return SD_OK;
+  int grid = 2 * units < num_sms() ? 2 * units : (num_sms() & ~1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_mc_kernel<EPI, MAX_BN>, P);
+  count_launch();
+  static const bool sync_debug = getenv("SD_SYNC_DEBUG") != nullptr;
+  if (e == cudaSuccess && sync_debug) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess)
+    return fail(SD_ERR_CUDA, "gemm_tc_mc_kernel<EPI=%d,MAX_BN=%d> n_tile=%d kiters=%d units=%d: %s", EPI, MAX_BN,
+                P.n_tile, P.num_kiters, units, cudaGetErrorString(e));
+  return SD_OK;
+}
+
 // Chooses the shared-memory configuration from n_tile.
 template <int EPI>
 inline int launch_gemm(const GemmParams& P, cudaStream_t stream) {

@@ -567,7 +567,7 @@ struct PipeState {
   uint32_t bphase = 0;  // EPI_CONV3: phase of the resident-weights barrier (one use per GEMM)
 };
 
-template <int EPI, int MAX_BN>
+template <int EPI, int MAX_BN, bool MC = false>
 __device__ __forceinline__ void gemm_setup(uint8_t* smem, GemmCtx& c) {
   using Cfg = GemmCfg<EPI, MAX_BN>;
   // 1024-byte alignment is required by the 128-byte swizzle atoms.  It is declared on the array
@@ -590,7 +590,7 @@ __device__ __forceinline__ void gemm_setup(uint8_t* smem, GemmCtx& c) {
     if (c.lane == 0) {
       for (int s = 0; s < Cfg::STAGES; ++s) {
         mbar_init(&c.full_bar[s], 1);
-        mbar_init(&c.empty_bar[s], 1);
+        mbar_init(&c.empty_bar[s], MC ? 2 : 1);  // MC: both CTAs of the pair must release a stage
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&c.tfull_bar[s], 1);
@@ -606,13 +606,16 @@ __device__ __forceinline__ void gemm_setup(uint8_t* smem, GemmCtx& c) {
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   c.tmem_base = *tmem_slot;
 }
 
+template <bool MC = false>
 __device__ __forceinline__ void gemm_teardown(const GemmCtx& c) {
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers
   if (c.warp == 0) {
     tc_fence_after();
     tmem_dealloc(c.tmem_base, TMEM_COLS);
@@ -620,7 +623,10 @@ __device__ __forceinline__ void gemm_teardown(const GemmCtx& c) {
 }
 
 // One GEMM: every role walks this CTA's tiles (tile = blockIdx.x, + gridDim.x, ...).
-template <int EPI, int MAX_BN>
+// MC = 2-CTA cluster with TMA multicast of the B (weight) tile: the two CTAs of a pair work on adjacent
+// m blocks of the same n block in lockstep; each loads HALF of the B tile and multicasts it to both, so a
+// CTA pulls 32 KB instead of 48 KB per k-iteration through L2 (the large GEMMs are L2 -> SM bound).
+template <int EPI, int MAX_BN, bool MC = false>
 __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, PipeState& ps) {
   using Cfg = GemmCfg<EPI, MAX_BN>;
   uint8_t* const smem = c.smem;
@@ -632,7 +638,11 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
   const int warp = c.warp, lane = c.lane;
   const int k_splits = P.k_splits < 1 ? 1 : P.k_splits;
   const int k_per = (P.num_kiters + k_splits - 1) / k_splits;
-  const int num_tiles = P.num_m_blocks * P.num_n_blocks * k_splits;  // split index fastest
+  const int crank = MC ? static_cast<int>(cluster_ctarank()) : 0;
+  const int m_units = MC ? (P.num_m_blocks + 1) / 2 : P.num_m_blocks;      // MC: pairs of m blocks
+  const int num_tiles = m_units * P.num_n_blocks * k_splits;               // split index fastest
+  const int tile0 = MC ? (blockIdx.x >> 1) : blockIdx.x;
+  const int tstep = MC ? (gridDim.x >> 1) : gridDim.x;
   const int acc_stages = (P.acc_slots * P.n_tile <= 256) ? 2 : 1;
   const uint32_t tmem_base = c.tmem_base;
   const int n_sub = P.n_sub < 1 ? 1 : P.n_sub;
@@ -656,7 +666,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
         const int box_rows = BM + (P.conv_taps - 1) * P.conv_dil;
         const uint32_t txa = static_cast<uint32_t>(box_rows) * BK * 2;
         const int row_shift = -(P.conv_taps / 2) * P.conv_dil;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tstep) {
           const int m_blk = tile / P.num_n_blocks;
           for (int kc = 0; kc < P.num_kiters; ++kc) {
             mbar_wait(&c.empty_bar[ps.stage], ps.phase ^ 1);
@@ -667,10 +677,11 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
           }
         }
       } else
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
         const int ot = tile / k_splits, ks = tile - ot * k_splits;
-        const int m_blk = ot / P.num_n_blocks;
-        const int n_blk = ot - m_blk * P.num_n_blocks;
+        const int m_unit = ot / P.num_n_blocks;
+        const int n_blk = ot - m_unit * P.num_n_blocks;
+        const int m_blk = MC ? 2 * m_unit + crank : m_unit;
         const int k_begin = ks * k_per, k_end = min(P.num_kiters, k_begin + k_per);
         for (int sub = 0; sub < n_sub; ++sub) {
           const int b_row = n_blk * b_row_stride + sub * P.n_tile;
@@ -689,7 +700,14 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
             uint8_t* sa = smem + ps.stage * Cfg::STAGE_BYTES;
             tma_load_2d(sa, &P.tmapA, &c.full_bar[ps.stage], P.kit[k].a_col,
                         P.a_row_base + m_blk * BM + P.kit[k].a_row_off);
-            tma_load_2d(sa + Cfg::A_BYTES, &P.tmapB, &c.full_bar[ps.stage], P.kit[k].b_col, b_row);
+            if (MC) {
+              // this CTA's half of the B tile, delivered to both CTAs of the pair
+              const int half_rows = P.n_tile >> 1;
+              tma_load_2d_mc(sa + Cfg::A_BYTES + crank * half_rows * (BK * 2), &P.tmapB, &c.full_bar[ps.stage],
+                             P.kit[k].b_col, b_row + crank * half_rows, 0x3);
+            } else {
+              tma_load_2d(sa + Cfg::A_BYTES, &P.tmapB, &c.full_bar[ps.stage], P.kit[k].b_col, b_row);
+            }
             if (++ps.stage == Cfg::STAGES) { ps.stage = 0; ps.phase ^= 1; }
           }
         }
@@ -702,7 +720,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       ps.bphase ^= 1;
       tc_fence_after();
       const uint32_t bres_addr = smem_u32(bres);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
         mbar_wait(&c.tempty_bar[ps.as], ps.aphase ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + ps.as * 256;
@@ -725,7 +743,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
         if (++ps.as == acc_stages) { ps.as = 0; ps.aphase ^= 1; }
       }
     } else if (lane == 0) {
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+      for (int tile = tile0; tile < num_tiles; tile += tstep)
       for (int sub = 0; sub < n_sub; ++sub) {
         const int ks = tile % k_splits;
         const int k_begin = ks * k_per, k_end = min(P.num_kiters, k_begin + k_per);
@@ -746,7 +764,8 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
             umma_f16(d_addr, da + 2 * kk, db + 2 * kk, P.idesc,
                      ((k > k_begin && P.kit[k].accum) || kk) ? 1u : 0u);
           }
-          umma_commit(&c.empty_bar[ps.stage]);  // frees the smem slot once these MMAs retire
+          if (MC) umma_commit_mc(&c.empty_bar[ps.stage], 0x3);  // the slot is free once BOTH CTAs' MMAs retire
+          else umma_commit(&c.empty_bar[ps.stage]);            // frees the smem slot once these MMAs retire
           if (++ps.stage == Cfg::STAGES) { ps.stage = 0; ps.phase ^= 1; }
         }
         umma_commit(&c.tfull_bar[ps.as]);  // accumulator complete -> epilogue
@@ -760,11 +779,12 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
     const int et = threadIdx.x - 64;
     int last_n_blk = -1;
     PoolState pool_state;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    for (int tile = tile0; tile < num_tiles; tile += tstep)
     for (int sub = 0; sub < n_sub; ++sub) {
       const int ot = tile / k_splits, ksplit = tile - ot * k_splits;
-      const int m_blk = ot / P.num_n_blocks;
-      const int n_blk = ot - m_blk * P.num_n_blocks;
+      const int m_unit = ot / P.num_n_blocks;
+      const int n_blk = ot - m_unit * P.num_n_blocks;
+      const int m_blk = MC ? 2 * m_unit + crank : m_unit;
       if ((epi_is_tdnn(EPI) || EPI == EPI_ATT) && n_blk != last_n_blk) {
         // stage this n block's per-column constants (the previous tile's readers all passed the
         // "staging complete" barrier below, so the table may be overwritten)
@@ -826,6 +846,18 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
   gemm_setup<EPI, MAX_BN>(smem, c);
   gemm_run<EPI, MAX_BN>(P, c, ps);
   gemm_teardown(c);
+}
+
+// The same GEMM on 2-CTA clusters with the B tile multicast (launched with cluster dims {2,1,1}).
+template <int EPI, int MAX_BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_mc_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  GemmCtx c;
+  PipeState ps;
+  gemm_setup<EPI, MAX_BN, true>(smem, c);
+  gemm_run<EPI, MAX_BN, true>(P, c, ps);
+  gemm_teardown<true>(c);
 }
 
 // A CHAIN of dependent GEMMs in one cooperative launch: step s+1 reads what step s wrote
