@@ -98,6 +98,7 @@ struct SdEcapaPlan {
   // SD_ECAPA_MC=1: 256-wide GEMMs on 2-CTA clusters with the weight tile multicast.  Correct, but only ~3% faster
   // on the MFA layer and neutral elsewhere (the GEMMs are bound by per-SM operand ingest, not by L2), so off.
   bool use_mc = false;
+  bool use_2sm = true;     // SD_ECAPA_2SM=0: 256-wide GEMMs with cta_group::1 instead of CTA pairs
   bool use_conv3 = true;   // SD_ECAPA_CONV3=0: Res2Net convs through the generic tap-per-k-iteration path
   bool use_graph = true;   // SD_ECAPA_GRAPH=0 disables CUDA-graph replay of the trunk
   cudaStream_t cap_stream = nullptr;
@@ -187,7 +188,7 @@ int setup_tdnn_gemm(GemmParams& P, const __half* A, long rows, int a_cols, int l
   P.num_n_blocks = cout / n_tile;
   P.n_tile = n_tile;
   P.idesc = make_idesc_f16(n_tile, 0);
-  int ki = 0;
+  int ki = 0;  // (the cta_group::2 launch re-encodes idesc with M = 256, see build_program)
   for (int j = 0; j < taps; ++j)
     for (int c = 0; c < cin_p / BK; ++c, ++ki) {
       P.kit[ki].a_col = a_col0 + c * BK;
@@ -236,14 +237,14 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   const long R = pr.rows;
   // block0: k = 5 over the 128-padded mel channels
   SD_TRY(setup_tdnn_gemm(pr.block0, p->feats, R, FEAT_P, FEAT_P, p->w0, C1, 5 * FEAT_P, 256, FEAT_P,
-                         5, 1, 0, pr, p->x0, C1, 0, EF_REFLECT, p->use_mc));
+                         5, 1, 0, pr, p->x0, C1, 0, EF_REFLECT, p->use_mc || p->use_2sm));
   for (int b = 0; b < 3; ++b) {
     const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
     const int ld_in = b == 0 ? C1 : C3;
     const BlockW& bw = p->blk[b];
     // tdnn1: 1x1, also copies sub-band 0 into v (Res2Net passes it through)
     SD_TRY(setup_tdnn_gemm(pr.tdnn1[b], in, R, C1, ld_in, bw.tdnn1, C1, C1, 256, C1, 1, 1, 0, pr,
-                           p->u, C1, 0, 0, p->use_mc));
+                           p->u, C1, 0, 0, p->use_mc || p->use_2sm));
     pr.tdnn1[b].epi.out2 = p->v;
     pr.tdnn1[b].epi.ld_out2 = C1;
     pr.tdnn1[b].epi.out2_cols = SUB;
@@ -273,10 +274,10 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
       Cv.conv_cin = SUB;
     }
     SD_TRY(setup_tdnn_gemm(pr.tdnn2[b], p->v, R, C1, C1, bw.tdnn2, C1, C1, 256, C1, 1, 1, 0, pr,
-                           p->w, C1, 0, 0, p->use_mc));
+                           p->w, C1, 0, 0, p->use_mc || p->use_2sm));
   }
   SD_TRY(setup_tdnn_gemm(pr.mfa, p->cat, R, C3, C3, p->wmfa, C3, C3, 256, C3, 1, 1, 0, pr, p->h, C3,
-                         0, 0, p->use_mc));
+                         0, 0, p->use_mc || p->use_2sm));
   SD_TRY(setup_tdnn_gemm(pr.att, p->h, R, C3, C3, p->watt, ATT, C3, 128, C3, 1, 1, 0, pr, p->attn,
                          ATT, 0, 0));
   pr.att.epi.utt_bias = p->uttbias;
@@ -362,6 +363,11 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     P.epi.pooled_h = p->pooled_h;
     P.epi.C = C3;
   }
+  if (p->use_2sm) {
+    pr.block0.idesc = make_idesc_f16(256, 0, 256);
+    pr.mfa.idesc = make_idesc_f16(256, 0, 256);
+    for (int b = 0; b < 3; ++b) pr.tdnn1[b].idesc = pr.tdnn2[b].idesc = make_idesc_f16(256, 0, 256);
+  }
   {
     std::vector<GemmParams> chain;
     for (int b = 0; b < 3; ++b) {
@@ -399,6 +405,7 @@ void mark(SdEcapaPlan* p, cudaStream_t st) {
 
 // the 256-wide TDNN GEMMs (block0, tdnn1/2, MFA): 2-CTA multicast variant unless disabled
 int launch_big(SdEcapaPlan* p, const GemmParams& P, cudaStream_t st) {
+  if (p->use_2sm) return launch_gemm_2sm(P, st);
   if (p->use_mc) return launch_gemm_mc_t<EPI_TDNN, 256>(P, st);
   return launch_gemm<EPI_TDNN>(P, st);
 }
@@ -526,7 +533,9 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   if (const char* e = getenv("SD_ECAPA_GRAPH")) p->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_CONV3")) p->use_conv3 = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_MC")) p->use_mc = atoi(e) != 0;
-  if (p->use_chain) p->use_mc = false;  // the cooperative chain uses the plain kernels
+  if (const char* e = getenv("SD_ECAPA_2SM")) p->use_2sm = atoi(e) != 0;
+  if (p->use_chain) p->use_mc = p->use_2sm = false;  // the cooperative chain uses the plain kernels
+  if (p->use_2sm) p->use_mc = false;
   p->max_samples = max_samples;
   const int maxT = 1 + max_samples / 160;
   p->max_rows = (long)max_batch * tp_of(maxT);

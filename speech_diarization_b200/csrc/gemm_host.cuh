@@ -138,6 +138,42 @@ inline int launch_gemm_mc_t(const GemmParams& P, cudaStream_t stream) {
   return SD_OK;
 }
 
+// cta_group::2 launch (gemm_tc_2sm_kernel): EPI_TDNN, n_tile = 256, idesc with M = 256, tmapB box = 128 rows.
+inline int launch_gemm_2sm(const GemmParams& P, cudaStream_t stream) {
+  using Cfg = Cfg2sm;
+  if (P.n_tile != 256 || P.num_kiters < 1 || P.num_kiters > MAX_KITERS) return SD_ERR_ARG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_2sm_kernel<EPI_TDNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+        cudaSuccess)
+      return SD_ERR_CUDA;
+    attr_set = true;
+  }
+  const int units = ((P.num_m_blocks + 1) / 2) * P.num_n_blocks;
+  if (units <= 0) return SD_OK;
+  const int grid = 2 * units < num_sms() ? 2 * units : (num_sms() & ~1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI_TDNN>, P);
+  count_launch();
+  static const bool sync_debug = getenv("SD_SYNC_DEBUG") != nullptr;
+  if (e == cudaSuccess && sync_debug) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess)
+    return fail(SD_ERR_CUDA, "gemm_tc_2sm_kernel n_tile=%d kiters=%d units=%d: %s", P.n_tile, P.num_kiters, units,
+                cudaGetErrorString(e));
+  return SD_OK;
+}
+
 // Chooses the shared-memory configuration from n_tile.
 template <int EPI>
 inline int launch_gemm(const GemmParams& P, cudaStream_t stream) {

@@ -860,6 +860,164 @@ gemm_tc_mc_kernel(const __grid_constant__ GemmParams P) {
   gemm_teardown<true>(c);
 }
 
+// ------------------------------------------------------------------------------------------------
+// cta_group::2 variant for the 256-wide TDNN GEMMs (block0, tdnn1/2, MFA): two CTAs (a cluster) own a
+// 256 x 256 output tile.  Each loads ITS 128 rows of A and ITS 128 rows of B per k-iteration (32 KB
+// instead of 48 KB of operand ingest per SM — the 1-CTA kernel is bound by that ingest, not by the
+// tensor pipe), the LEADER's single thread issues tcgen05.mma.cta_group::2 (M = 256), and each CTA's
+// TMEM receives the accumulators of its own 128 rows, which its own epilogue warps drain as before.
+//   full[s]   leader only   <- TMA complete_tx from BOTH CTAs (+ the leader's expect_tx arrive)
+//   empty[s]  both CTAs     <- leader's tcgen05.commit (multicast to both)
+//   tfull[a]  both CTAs     <- leader's tcgen05.commit after a tile's last MMA (multicast)
+//   tempty[a] leader only   <- 16 arrivals: the 8 epilogue warps of each CTA
+struct Cfg2sm {
+  static constexpr int A_BYTES = BM * BK * 2;             // 16 KB: this CTA's 128 rows of A
+  static constexpr int B_BYTES = 128 * BK * 2;            // 16 KB: this CTA's half of the 256-row B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
+  static constexpr int STAGES = 4;
+  static constexpr int OUT_STAGE_BYTES = 65536;
+  static constexpr int EPI_BYTES = 3 * 256 * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + EPI_BYTES + 256;
+};
+
+template <int EPI>  // EPI_TDNN only (a template so the header can be included from several translation units)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
+  static_assert(EPI == EPI_TDNN, "the cta_group::2 kernel carries the TDNN epilogue");
+  using Cfg = Cfg2sm;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* const stage_out = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  float* const epi_sp = reinterpret_cast<float*>(stage_out + Cfg::OUT_STAGE_BYTES);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(stage_out + Cfg::OUT_STAGE_BYTES + Cfg::EPI_BYTES);
+  uint64_t* const full_bar = bars;                    // [STAGES]  (used in the leader)
+  uint64_t* const empty_bar = bars + Cfg::STAGES;     // [STAGES]
+  uint64_t* const tfull_bar = bars + 2 * Cfg::STAGES; // [2]
+  uint64_t* const tempty_bar = tfull_bar + 2;         // [2]       (used in the leader)
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(cluster_ctarank());
+  const bool leader = crank == 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&P.tmapA);
+      tma_prefetch_desc(&P.tmapB);
+      for (int s = 0; s < Cfg::STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tfull_bar[s], 1);
+        mbar_init(&tempty_bar[s], 2 * EPI_WARPS);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_units = (P.num_m_blocks + 1) / 2;
+  const int num_tiles = m_units * P.num_n_blocks;
+  const int tile0 = blockIdx.x >> 1, tstep = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        const int m_unit = tile / P.num_n_blocks;
+        const int n_blk = tile - m_unit * P.num_n_blocks;
+        const int m_blk = 2 * m_unit + crank;
+        for (int k = 0; k < P.num_kiters; ++k) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          tma_load_2d_2sm(sa, &P.tmapA, &full_bar[stage], P.kit[k].a_col,
+                          P.a_row_base + m_blk * BM + P.kit[k].a_row_off);
+          tma_load_2d_2sm(sa + Cfg::A_BYTES, &P.tmapB, &full_bar[stage], P.kit[k].b_col,
+                          n_blk * P.n_tile + crank * 128);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc = P.idesc;  // encoded with M = 256 by the host
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * 256;
+        for (int k = 0; k < P.num_kiters; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = make_smem_desc_sw128(a_addr);
+          const uint64_t db = make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk)
+            umma_f16_2sm(acc, da + 2 * kk, db + 2 * kk, idesc, (P.kit[k].accum | kk) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 0x3);  // frees this stage in BOTH CTAs
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull_bar[as], 0x3);       // accumulators complete in both CTAs' TMEM
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;
+    int last_n_blk = -1, as = 0;
+    uint32_t aphase = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
+      const int m_unit = tile / P.num_n_blocks;
+      const int n_blk = tile - m_unit * P.num_n_blocks;
+      const int m_blk = 2 * m_unit + crank;
+      if (n_blk != last_n_blk) {
+        last_n_blk = n_blk;
+        for (int i = et; i < P.n_tile; i += EPI_THREADS) {
+          const int col = n_blk * P.n_tile + i;
+          const bool ok = col < P.epi.N_cols;
+          epi_sp[i] = (ok && P.epi.bias) ? P.epi.bias[col] : 0.f;
+          epi_sp[256 + i] = (ok && P.epi.scale) ? P.epi.scale[col] : 1.f;
+          epi_sp[512 + i] = (ok && P.epi.shift) ? P.epi.shift[col] : 0.f;
+        }
+        epi_named_barrier();
+      }
+      uint4 pre[2][4];
+      tdnn_prefetch(P, m_blk, n_blk, quarter, half, lane, pre);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + as * 256;
+      epi_named_barrier();  // every thread has finished writing out the previous tile's staging
+      epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre, stage_out);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);  // this CTA's share of the accumulator is drained
+      if (++as == 2) { as = 0; aphase ^= 1; }
+      epi_named_barrier();  // staging tile complete
+      tdnn_writeout(P, m_blk, n_blk, stage_out, et);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while the peer may still signal its barriers
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 // A CHAIN of dependent GEMMs in one cooperative launch: step s+1 reads what step s wrote
 // (Res2Net: y_i = TDNN_i(x_i + y_{i-1}); around it the block's two 1x1 TDNNs).  Between steps
 // the whole grid synchronises; the generic-proxy stores of the epilogues are made visible to
