@@ -8,8 +8,8 @@ python tools/ncu_target.py > gpurun_out/ncu_plain.log 2>&1 || { tail -5 gpurun_o
 N='--set full --clock-control none --import-source on --kernel-name-base demangled'
 for what in "$@"; do
 case $what in
- mfa)   ncu $N -k 'regex:gemm_tc_kernel<\(int\)1, \(int\)256>' -s 15 -c 1 -o gpurun_out/prof_mfa python tools/ncu_target.py > gpurun_out/ncu_mfa.log 2>&1;;
- tdnn2) ncu $N -k 'regex:gemm_tc_kernel<\(int\)1, \(int\)256>' -s 10 -c 1 -o gpurun_out/prof_tdnn2 python tools/ncu_target.py > gpurun_out/ncu_tdnn2.log 2>&1;;
+ mfa)   ncu $N -k 'regex:gemm_tc_2sm_kernel' -s 15 -c 1 -o gpurun_out/prof_mfa python tools/ncu_target.py > gpurun_out/ncu_mfa.log 2>&1;;
+ tdnn2) ncu $N -k 'regex:gemm_tc_2sm_kernel' -s 10 -c 1 -o gpurun_out/prof_tdnn2 python tools/ncu_target.py > gpurun_out/ncu_tdnn2.log 2>&1;;
  res)   ncu $N -k 'regex:gemm_tc_kernel<\(int\)5, \(int\)128>' -s 24 -c 1 -o gpurun_out/prof_res2net python tools/ncu_target.py > gpurun_out/ncu_res.log 2>&1;;
  att)   ncu $N -k 'regex:gemm_tc_kernel<\(int\)4, \(int\)128>' -s 1 -c 1 -o gpurun_out/prof_att python tools/ncu_target.py > gpurun_out/ncu_att.log 2>&1;;
  pool)  ncu $N -k 'regex:gemm_tc_kernel<\(int\)2, \(int\)256>' -s 1 -c 1 -o gpurun_out/prof_pool python tools/ncu_target.py > gpurun_out/ncu_pool.log 2>&1;;
