@@ -222,7 +222,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     *out = &it->second;
     return SD_OK;
   }
-  if (p->programs.size() > 64) {
+  if (p->programs.size() > 256) {   // variable-length callers (embed_segments) produce many (B, T) shapes
     cudaDeviceSynchronize();  // launches that reference the cached descriptors may still be in flight
     for (auto& kv : p->programs)
       if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
@@ -368,7 +368,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     pr.mfa.idesc = make_idesc_f16(256, 0, 256);
     for (int b = 0; b < 3; ++b) pr.tdnn1[b].idesc = pr.tdnn2[b].idesc = make_idesc_f16(256, 0, 256);
   }
-  {
+  if (p->use_chain) {   // device copy of the step table, only for the cooperative chain variant
     std::vector<GemmParams> chain;
     for (int b = 0; b < 3; ++b) {
       chain.push_back(pr.tdnn1[b]);
@@ -481,7 +481,7 @@ int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStr
   if (can_graph && pr.graph) {
     SD_CUDA_OK(cudaGraphLaunch(pr.graph, st));
     count_launch(pr.graph_launches);
-  } else if (can_graph && pr.runs >= 1) {
+  } else if (can_graph && pr.runs >= 2) {   // capture on the third use: one-off shapes are not worth ~1 ms
     const long before = launch_counter().load();
     cudaGraph_t g = nullptr;
     // capture on a plan-owned stream (the caller's may be the legacy default stream, which cannot
