@@ -162,6 +162,16 @@ int sd_ahc_average_f32(const float* dist_dev, int N, double threshold, int32_t* 
  * number of reciprocal-nearest-neighbour rounds and of merges performed. */
 int sd_ahc_read_stats(const void* workspace_dev, int N, int32_t* rounds, int32_t* merges);
 
+/* Centroid-linkage agglomerative clustering: the linkage matrix
+ * scipy.cluster.hierarchy.linkage(X, method="centroid", metric="euclidean") computes inside pyannote's
+ * AgglomerativeClustering, which diarization_baseline.py:176-180,252-257 drives through
+ * `pipeline.clustering.threshold`.  x_dev [N, D] f32 (pyannote passes unit-normalised embeddings).
+ * Z_dev [N-1, 4] f64 in scipy's layout: (cluster id a < b, cluster id b, centroid distance, size); ids
+ * >= N name earlier merges.  Merges are taken strictly in order of the global minimum (centroid linkage is
+ * not monotone; inversions are kept).  workspace_dev: sd_centroid_linkage_workspace_bytes(N, D) bytes. */
+size_t sd_centroid_linkage_workspace_bytes(int N, int D);
+int sd_centroid_linkage_f64(const float* x_dev, int N, int D, double* Z_dev, void* workspace_dev, void* stream);
+
 /* best[i] = argmax_k <x_i, c_k>, score[i] = that maximum (frame_reassign,
  * anti_stick_diarize.py:433-434).  x_dev [N, D], cent_dev [K, D], K <= 64.
  * First maximum wins, as numpy.argmax. score_dev may be NULL. */

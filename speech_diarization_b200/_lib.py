@@ -41,6 +41,8 @@ SIGNATURES = {
     "sd_ahc_workspace_bytes": (c_size_t, [c_int]),
     "sd_ahc_average_f32": (c_int, [c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sd_ahc_read_stats": (c_int, [c_void_p, c_int, POINTER(c_int32), POINTER(c_int32)]),
+    "sd_centroid_linkage_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "sd_centroid_linkage_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sd_window_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sd_adjacent_cosine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sd_debug_gemm_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

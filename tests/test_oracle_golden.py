@@ -163,3 +163,18 @@ def test_product_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(_lib.SdError):
         speech_encode.fbank_batch(np.zeros((1, 4000), np.float32))
+
+
+def test_product_fcluster_distance_matches_scipy_with_inversions():
+    """Host-side flat cut of a centroid linkage (speech_diarization_b200.diarization_baseline.fcluster_distance)
+    against scipy.cluster.hierarchy.fcluster(criterion="distance") on dendrograms WITH inversions."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    from speech_diarization_b200.diarization_baseline import fcluster_distance
+    rng = np.random.default_rng(0)
+    for n in (2, 5, 50, 400):
+        X = rng.standard_normal((n, 8))
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        Z = linkage(X, "centroid", "euclidean")
+        for t in (0.0, 0.3, 0.7, 1.0, 1.2, 5.0):
+            assert co.same_partition(fcluster(Z, t, "distance") - 1, fcluster_distance(Z, t)), (n, t)
+    assert (np.diff(Z[:, 2]) < 0).any()
