@@ -1,7 +1,7 @@
 // ecapa_kernels.cuh — the non-GEMM kernels of the ECAPA-TDNN trunk:
 // squeeze-excitation (time mean -> 2-layer MLP -> scale + residual), the global
-// statistics of attentive pooling, and the small dense layers that act once per
-// utterance.  All are bandwidth-bound reductions over the f16 channels-last
+// statistics of attentive pooling, and the split-K reductions of the per-utterance
+// dense layers.  All are bandwidth-bound reductions over the f16 channels-last
 // activation tensors [B*Tp, C] written by the GEMM epilogues (gemm_tc.cuh).
 //
 // Reference arithmetic: speechbrain SEBlock / AttentiveStatisticsPooling /
@@ -194,39 +194,6 @@ se_apply_kernel(const __half* __restrict__ w, int ld_w, const float* __restrict_
       oh[e] = __floats2half2_rn(fmaf(a.x, sc[2 * e], q.x), fmaf(a.y, sc[2 * e + 1], q.y));
     }
     *reinterpret_cast<uint4*>(out + r * ld_out + c) = ov;
-  }
-}
-
-// Y[b, o] = bias[o] + sum_k W[o, k] * X[b, k]   (per-utterance dense layer, f32).
-// One CTA handles UB = 4 utterances so each weight row is read once per 4 outputs rows.
-// grid ceil(B/4), block 256 (8 warps; warp w owns outputs w, w+8, ...).  K % 4 == 0.
-__global__ void __launch_bounds__(256)
-dense_rows_kernel(const float* __restrict__ W, const float* __restrict__ bias,
-                  const float* __restrict__ X, int B, int K, int O, float* __restrict__ Y) {
-  const int b0 = blockIdx.x * 4;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nb = min(4, B - b0);
-  const float4* x[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u)
-    x[u] = reinterpret_cast<const float4*>(X + static_cast<size_t>(b0 + (u < nb ? u : 0)) * K);
-  for (int o = warp; o < O; o += 8) {
-    const float4* w = reinterpret_cast<const float4*>(W + static_cast<size_t>(o) * K);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = lane; i < K / 4; i += 32) {
-      const float4 wv = __ldg(w + i);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4 xv = __ldg(x[u] + i);
-        acc[u] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
-    if (lane == 0) {
-      const float bo = bias ? bias[o] : 0.f;
-      for (int u = 0; u < nb; ++u) Y[static_cast<size_t>(b0 + u) * O + o] = acc[u] + bo;
-    }
   }
 }
 
