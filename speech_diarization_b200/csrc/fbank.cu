@@ -335,12 +335,15 @@ static void build_tables(int variant, FbankTables& t) {
   }
 }
 
-static FbankTables* g_tab[2] = {nullptr, nullptr};
+static FbankTables* g_tab[64][2] = {};   // per device, per variant
 static std::mutex g_tab_mu;
 
 static int get_tables(int variant, FbankTables** out) {
   std::lock_guard<std::mutex> lk(g_tab_mu);
-  if (!g_tab[variant]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!g_tab[dev][variant]) {
     FbankTables* h = new FbankTables;
     build_tables(variant, *h);
     FbankTables* d = nullptr;
@@ -348,9 +351,9 @@ static int get_tables(int variant, FbankTables** out) {
     if (e == cudaSuccess) e = cudaMemcpy(d, h, sizeof(FbankTables), cudaMemcpyHostToDevice);
     delete h;
     if (e != cudaSuccess) return fail(SD_ERR_CUDA, "fbank tables: %s", cudaGetErrorString(e));
-    g_tab[variant] = d;
+    g_tab[dev][variant] = d;
   }
-  *out = g_tab[variant];
+  *out = g_tab[dev][variant];
   return SD_OK;
 }
 
@@ -363,13 +366,15 @@ int fbank_launch(const float* wav, long wav_stride, int B, int n_samples, int va
   const int T = 1 + n_samples / HOP;
   FbankTables* tab = nullptr;
   SD_TRY(get_tables(variant, &tab));
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 63]) {   // per device
     SD_CUDA_OK(cudaFuncSetAttribute(fbank_frames_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(sizeof(FbankSmem))));
     SD_CUDA_OK(cudaFuncSetAttribute(fbank_frames_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(sizeof(FbankSmem))));
-    attr = true;
+    attr[dev & 63] = true;
   }
   dim3 grid((T + FR_PER_CTA - 1) / FR_PER_CTA, B);
   if (variant == 0)

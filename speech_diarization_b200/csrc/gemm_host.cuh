@@ -66,6 +66,16 @@ inline int make_tmap_f16_interior(CUtensorMap* m, const void* base, long ld, int
   return r == CUDA_SUCCESS ? SD_OK : SD_ERR_DRIVER;
 }
 
+// cudaFuncSetAttribute is per device: remember which devices already have it for a given kernel
+inline bool attr_needed(bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 inline int num_sms() {
   static int n = 0;
   if (!n) {
@@ -80,14 +90,11 @@ inline int num_sms() {
 template <int EPI, int MAX_BN>
 inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
   using Cfg = GemmCfg<EPI, MAX_BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<EPI, MAX_BN>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Cfg::SMEM_BYTES) != cudaSuccess)
-      return SD_ERR_CUDA;
-    attr_set = true;
-  }
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done) &&
+      cudaFuncSetAttribute(gemm_tc_kernel<EPI, MAX_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           Cfg::SMEM_BYTES) != cudaSuccess)
+    return SD_ERR_CUDA;
   const int tiles = P.num_m_blocks * P.num_n_blocks * (P.k_splits > 1 ? P.k_splits : 1);
   if (tiles <= 0) return SD_OK;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -106,13 +113,11 @@ inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
 template <int EPI, int MAX_BN>
 inline int launch_gemm_mc_t(const GemmParams& P, cudaStream_t stream) {
   using Cfg = GemmCfg<EPI, MAX_BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_mc_kernel<EPI, MAX_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Cfg::SMEM_BYTES) != cudaSuccess)
-      return SD_ERR_CUDA;
-    attr_set = true;
-  }
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done) &&
+      cudaFuncSetAttribute(gemm_tc_mc_kernel<EPI, MAX_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           Cfg::SMEM_BYTES) != cudaSuccess)
+    return SD_ERR_CUDA;
   const int units = ((P.num_m_blocks + 1) / 2) * P.num_n_blocks;
   if (units <= 0) return SD_OK;
   int grid = 2 * units < num_sms() ? 2 * units : (num_sms() & ~1);
@@ -142,13 +147,11 @@ inline int launch_gemm_mc_t(const GemmParams& P, cudaStream_t stream) {
 inline int launch_gemm_2sm(const GemmParams& P, cudaStream_t stream) {
   using Cfg = Cfg2sm;
   if (P.n_tile != 256 || P.num_kiters < 1 || P.num_kiters > MAX_KITERS) return SD_ERR_ARG;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_2sm_kernel<EPI_TDNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
-        cudaSuccess)
-      return SD_ERR_CUDA;
-    attr_set = true;
-  }
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done) &&
+      cudaFuncSetAttribute(gemm_tc_2sm_kernel<EPI_TDNN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           Cfg::SMEM_BYTES) != cudaSuccess)
+    return SD_ERR_CUDA;
   const int units = ((P.num_m_blocks + 1) / 2) * P.num_n_blocks;
   if (units <= 0) return SD_OK;
   const int grid = 2 * units < num_sms() ? 2 * units : (num_sms() & ~1);
@@ -195,13 +198,11 @@ inline int launch_gemm(const GemmParams& P, cudaStream_t stream) {
 template <int EPI, int MAX_BN>
 inline int launch_gemm_chain(const GemmParams* dev_steps, int num_steps, cudaStream_t stream) {
   using Cfg = GemmCfg<EPI, MAX_BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_chain_kernel<EPI, MAX_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Cfg::SMEM_BYTES) != cudaSuccess)
-      return SD_ERR_CUDA;
-    attr_set = true;
-  }
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done) &&
+      cudaFuncSetAttribute(gemm_chain_kernel<EPI, MAX_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           Cfg::SMEM_BYTES) != cudaSuccess)
+    return SD_ERR_CUDA;
   void* args[] = {(void*)&dev_steps, (void*)&num_steps};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)gemm_chain_kernel<EPI, MAX_BN>, dim3(num_sms()),
                                               dim3(GEMM_THREADS), args, Cfg::SMEM_BYTES, stream);

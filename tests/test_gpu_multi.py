@@ -58,3 +58,21 @@ def test_two_gpu_pipeline_matches_single_gpu():
     single = clustering.cluster_embeddings_device(torch.from_numpy(ref).cuda(), 0.68).cpu().numpy()
     np.testing.assert_array_equal(res[0][2], single)
     assert res[0][3] == res[1][3] and len(res[0][3]) >= 1
+
+
+def test_one_process_two_devices():
+    """Two plans on two devices inside ONE process (per-device kernel attributes and fbank tables)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from speech_diarization_b200 import speech_encode, clustering
+    from speech_diarization_b200.weights import random_ecapa_state_dict
+    sd = random_ecapa_state_dict(0)
+    w = torch.from_numpy(synth_wave(8, 24000, 5))
+    outs = []
+    for d in (0, 1):
+        enc = speech_encode.EcapaEncoderB200(sd, device=f"cuda:{d}", max_batch=8, max_samples=24000)
+        outs.append(enc.encode_batch(w).squeeze(1).cpu())
+        x = torch.randn(300, 192, device=f"cuda:{d}")
+        assert clustering.cluster_embeddings_device(x, 0.68).device.index == d
+        enc.close()
+    assert torch.equal(outs[0], outs[1])
