@@ -28,6 +28,7 @@
 #include "ecapa_kernels.cuh"
 #include "fbank.cuh"
 #include "gemm_host.cuh"
+#include "res2net_fused.cuh"
 #include "sd_status.h"
 
 using namespace sd;
@@ -62,6 +63,8 @@ struct Program {     // launch parameters for one (B, T) shape
   long rows = 0;
   GemmParams block0, tdnn1[3], res[3][7], resc[3][7], tdnn2[3], mfa, ctx, att, pool, fc;  // resc: EPI_CONV3 form of res
   GemmParams* chain_dev = nullptr;  // device copy of [3][9]: tdnn1, 7 x Res2Net, tdnn2 per block
+  Res2Params r2[3];                 // the 7 Res2Net convs of a block as one launch (res2net_fused.cuh)
+  bool r2_ok = false;               // shape fits the fused kernel (16 <= T, T + 2*dil <= 168)
   cudaGraphExec_t graph = nullptr;  // captured trunk (block0 .. FC) for this shape
   int graph_launches = 0;
   int runs = 0;
@@ -99,6 +102,7 @@ struct SdEcapaPlan {
   // on the MFA layer and neutral elsewhere (the GEMMs are bound by per-SM operand ingest, not by L2), so off.
   bool use_mc = false;
   bool use_2sm = true;     // SD_ECAPA_2SM=0: 256-wide GEMMs with cta_group::1 instead of CTA pairs
+  bool use_r2fused = true; // SD_ECAPA_R2FUSED=0: Res2Net chain as 7 launches per block instead of one
   bool use_conv3 = true;   // SD_ECAPA_CONV3=0: Res2Net convs through the generic tap-per-k-iteration path
   bool use_graph = true;   // SD_ECAPA_GRAPH=0 disables CUDA-graph replay of the trunk
   cudaStream_t cap_stream = nullptr;
@@ -273,6 +277,27 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
       Cv.conv_dil = bw.dil;
       Cv.conv_cin = SUB;
     }
+    pr.r2_ok = T >= 16 && T + 2 * 4 <= R2_RA_MAX;
+    if (pr.r2_ok) {
+      Res2Params& Q = pr.r2[b];
+      memset(&Q, 0, sizeof(Q));
+      SD_TRY(make_tmap_f16(&Q.tmapU, p->u, R, C1, C1, T + 2 * bw.dil));
+      for (int i = 0; i < 7; ++i) {
+        SD_TRY(make_tmap_f16(&Q.tmapW[i], bw.res[i].W, SUB, 3 * SUB, 3 * SUB, SUB));
+        Q.bias[i] = bw.res[i].bias;
+        Q.scale[i] = bw.res[i].scale;
+        Q.shift[i] = bw.res[i].shift;
+      }
+      Q.u = p->u;
+      Q.v = p->v;
+      Q.ld = C1;
+      Q.B = B;
+      Q.T = T;
+      Q.Tp = pr.Tp;
+      Q.H = HALO;
+      Q.dil = bw.dil;
+      Q.idesc = make_idesc_f16(SUB, 0);
+    }
     SD_TRY(setup_tdnn_gemm(pr.tdnn2[b], p->v, R, C1, C1, bw.tdnn2, C1, C1, 256, C1, 1, 1, 0, pr,
                            p->w, C1, 0, 0, p->use_mc || p->use_2sm));
   }
@@ -403,6 +428,56 @@ void mark(SdEcapaPlan* p, cudaStream_t st) {
   cudaEventRecord(p->ev_pool[p->ev_used++], st);
 }
 
+int launch_res2net_fused(const Res2Params& Q, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  if (attr_needed(attr_done)) {
+    if (cudaFuncSetAttribute(res2net_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R2_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(res2net_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+      return fail(SD_ERR_CUDA, "res2net_fused_kernel attributes: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  const int grid = Q.B < 2 * num_sms() ? Q.B : 2 * num_sms();
+  if (grid <= 0) return SD_OK;
+  if (const char* path = getenv("SD_R2_TRACE")) {   // debug: dump CTA 0's per-conv clock stamps (no graph capture)
+    Res2Params T = Q;
+    long long* dev = nullptr;
+    std::vector<long long> host(32 * 18 + 32 * 4 * 8 + 32 * 12, 0);
+    if (cudaMalloc(&dev, host.size() * 8) != cudaSuccess) return SD_ERR_CUDA;
+    cudaMemsetAsync(dev, 0, host.size() * 8, st);
+    T.trace = dev;
+    res2net_fused_kernel<<<grid, R2_THREADS, R2_SMEM, st>>>(T);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host.data(), dev, host.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (FILE* f = fopen(path, "w")) {
+      for (int n = 0; n < 32; ++n) {
+        for (int k = 0; k < 18; ++k) fprintf(f, "%lld ", host[n * 18 + k] ? host[n * 18 + k] - host[0] : -1LL);
+        fprintf(f, "\n");
+      }
+      for (int n = 0; n < 32; ++n) {
+        for (int k = 0; k < 12; ++k) fprintf(f, "%lld ", host[1600 + n * 12 + k] ? host[1600 + n * 12 + k] - host[0] : -1LL);
+        fprintf(f, "\n");
+      }
+      for (int n = 0; n < 32 * 4; ++n) {
+        for (int k = 0; k < 8; ++k)
+          fprintf(f, "%lld ", host[32 * 18 + n * 8 + k] ? host[32 * 18 + n * 8 + k] - host[0] : -1LL);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    count_launch();
+    return SD_OK;
+  }
+  res2net_fused_kernel<<<grid, R2_THREADS, R2_SMEM, st>>>(Q);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  static const bool sync_debug = getenv("SD_SYNC_DEBUG") != nullptr;
+  if (e == cudaSuccess && sync_debug) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess)
+    return fail(SD_ERR_CUDA, "res2net_fused_kernel B=%d T=%d dil=%d: %s", Q.B, Q.T, Q.dil, cudaGetErrorString(e));
+  return SD_OK;
+}
+
 // the 256-wide TDNN GEMMs (block0, tdnn1/2, MFA): 2-CTA multicast variant unless disabled
 int launch_big(SdEcapaPlan* p, const GemmParams& P, cudaStream_t st) {
   if (p->use_2sm) return launch_gemm_2sm(P, st);
@@ -428,9 +503,13 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
     } else {
       SD_TRY(launch_big(p, pr.tdnn1[b], st));
       mark(p, st);
-      for (int i = 0; i < 7; ++i) {
-        if (p->use_conv3) SD_TRY(launch_gemm<EPI_CONV3>(pr.resc[b][i], st));
-        else SD_TRY(launch_gemm<EPI_TDNN>(pr.res[b][i], st));
+      if (p->use_r2fused && pr.r2_ok) {
+        SD_TRY(launch_res2net_fused(pr.r2[b], st));
+      } else {
+        for (int i = 0; i < 7; ++i) {
+          if (p->use_conv3) SD_TRY(launch_gemm<EPI_CONV3>(pr.resc[b][i], st));
+          else SD_TRY(launch_gemm<EPI_TDNN>(pr.res[b][i], st));
+        }
       }
       mark(p, st);
       SD_TRY(launch_big(p, pr.tdnn2[b], st));
@@ -532,6 +611,7 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   if (const char* e = getenv("SD_ECAPA_CHAIN")) p->use_chain = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_GRAPH")) p->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_CONV3")) p->use_conv3 = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_R2FUSED")) p->use_r2fused = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_MC")) p->use_mc = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_2SM")) p->use_2sm = atoi(e) != 0;
   if (p->use_chain) p->use_mc = p->use_2sm = false;  // the cooperative chain uses the plain kernels

@@ -39,6 +39,8 @@ constexpr int FR_PER_CTA = 32;
 constexpr int ZSTRIDE = 200;  // float2 per frame: 400 words = 16 mod 32, so the two frames of a half-warp in the
                               // 25-point stage (lane stride 25 float2) hit disjoint bank pairs
 constexpr int PSTRIDE = 204;  // floats per frame of power
+constexpr int SPAN = (FR_PER_CTA - 1) * HOP + NFFT;  // samples one CTA's frames cover (5360)
+static_assert(SPAN % 4 == 0 && SPAN <= FR_PER_CTA * PSTRIDE, "sample span must fit the aliased power buffer");
 
 struct FbankTables {
   float window[NFFT];
@@ -86,7 +88,6 @@ __device__ __forceinline__ float load_sample(const float* __restrict__ w, int i,
   if (VARIANT == 0) {  // reflect
     if (i < 0) i = -i;
     if (i >= n) i = 2 * (n - 1) - i;
-    return __ldg(w + i);
   }
   return (i >= 0 && i < n) ? __ldg(w + i) : 0.f;
 }
@@ -108,6 +109,27 @@ fbank_frames_kernel(const float* __restrict__ wav, long wav_stride, int n_sample
     uint32_t* dst = reinterpret_cast<uint32_t*>(&S.tab);
     for (int i = tid; i < static_cast<int>(sizeof(FbankTables) / 4); i += 256) dst[i] = src[i];
   }
+  // ---- step 0: stage the CTA's sample span (32 frames x hop + 240) in shared memory with 128-bit coalesced
+  // loads; the centre padding (reflect / zero) is resolved here, once per sample instead of once per FFT input.
+  // The span aliases the power buffer, which is not written before step 3.
+  float* xs = S.pw;
+  {
+    const int gs0 = f0 * HOP - NFFT / 2;
+    const bool aligned = (reinterpret_cast<uintptr_t>(w + gs0) & 15) == 0;
+    for (int i4 = tid; i4 < SPAN / 4; i4 += 256) {
+      const int g = gs0 + 4 * i4;
+      float4 v;
+      if (aligned && g >= 0 && g + 3 < n_samples) {
+        v = __ldg(reinterpret_cast<const float4*>(w + g));
+      } else {
+        v.x = load_sample<VARIANT>(w, g, n_samples);
+        v.y = load_sample<VARIANT>(w, g + 1, n_samples);
+        v.z = load_sample<VARIANT>(w, g + 2, n_samples);
+        v.w = load_sample<VARIANT>(w, g + 3, n_samples);
+      }
+      reinterpret_cast<float4*>(xs)[i4] = v;
+    }
+  }
   __syncthreads();
 
   // ---- step 1: 8-point DFTs over n1 for each (frame, n2); twiddle; store Y[k1*25 + n2]
@@ -117,13 +139,14 @@ fbank_frames_kernel(const float* __restrict__ wav, long wav_stride, int n_sample
     const int f = f0 + fl;
     float2 a[8];
     if (f < T) {
-      const int base = f * HOP - NFFT / 2;
+      const float* xf = xs + fl * HOP;
 #pragma unroll
       for (int n1 = 0; n1 < 8; ++n1) {
         const int n = 2 * (25 * n1 + n2);
         const float2 wn = *reinterpret_cast<const float2*>(&S.tab.window[n]);
-        a[n1].x = wn.x * load_sample<VARIANT>(w, base + n, n_samples);
-        a[n1].y = wn.y * load_sample<VARIANT>(w, base + n + 1, n_samples);
+        const float2 xv = *reinterpret_cast<const float2*>(xf + n);
+        a[n1].x = wn.x * xv.x;
+        a[n1].y = wn.y * xv.y;
       }
     } else {
 #pragma unroll
@@ -145,7 +168,7 @@ fbank_frames_kernel(const float* __restrict__ wav, long wav_stride, int n_sample
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) zf[k1 * 25 + n2] = cmul(X[k1], S.tab.tw200[k1 * 25 + n2]);
   }
-  __syncwarp();
+  __syncthreads();  // every warp is done with the staged samples before step 3 overwrites them with power
 
   // ---- step 2: 25-point DFT over n2 for each (frame, k1): lane = frame_local*8 + k1
   {

@@ -37,6 +37,30 @@ def test_trunk_layerwise_and_embedding_parity(oracle_model, encoder, B, T):
     assert _rel(got, ref) < 5e-3
 
 
+@pytest.mark.parametrize("B,T", [(300, 151), (5, 101), (3, 160), (2, 16), (9, 129), (4, 128), (2, 161)])
+def test_fused_res2net_is_bit_identical_to_the_per_conv_chain(oracle_model, B, T, monkeypatch):
+    """res2net_fused_kernel (one launch per block, inputs kept in shared memory) keeps the operand order and
+    f16 rounding points of the per-convolution chain, so v after every block and the embeddings must be
+    bit-identical.  B = 300 > 2 x 148 CTAs exercises the multi-window loop; T = 161 falls back."""
+    x = eo.synth_features(B, T, seed=7 * B + T)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SD_ECAPA_R2FUSED", fused)
+        monkeypatch.setenv("SD_ECAPA_GRAPH", "0")
+        enc = se.EcapaEncoderB200(oracle_model.state_dict(), device="cuda:0", max_batch=B, max_samples=(T - 1) * 160)
+        try:
+            emb = enc.forward_feats(x).cpu()
+            out[fused] = (emb, enc.debug_fetch("b3.res2net", B, T).cpu(), enc.debug_fetch("b3.out", B, T).cpu())
+        finally:
+            enc.close()
+    for a, b in zip(out["1"], out["0"]):
+        assert torch.equal(a, b)
+    with torch.inference_mode():
+        ref = oracle_model(x).squeeze(1)
+    cos = torch.nn.functional.cosine_similarity(out["1"][0], ref, dim=1)
+    assert float((1 - cos).max()) < COS_TOL
+
+
 @pytest.mark.parametrize("n", [24000, 16000, 4000, 8123, 48000, 160000])      # up to 10 s (pyannote chunk length)
 def test_encode_batch_matches_oracle(oracle_model, encoder, n):
     w = synth_wave(6, n, n)

@@ -11,6 +11,7 @@ case $what in
  mfa)   ncu $N -k 'regex:gemm_tc_2sm_kernel' -s 15 -c 1 -o gpurun_out/prof_mfa python tools/ncu_target.py > gpurun_out/ncu_mfa.log 2>&1;;
  tdnn2) ncu $N -k 'regex:gemm_tc_2sm_kernel' -s 10 -c 1 -o gpurun_out/prof_tdnn2 python tools/ncu_target.py > gpurun_out/ncu_tdnn2.log 2>&1;;
  res)   ncu $N -k 'regex:gemm_tc_kernel<\(int\)5, \(int\)128>' -s 24 -c 1 -o gpurun_out/prof_res2net python tools/ncu_target.py > gpurun_out/ncu_res.log 2>&1;;
+ r2f)   ncu $N -k 'regex:res2net_fused' -s 4 -c 1 -o gpurun_out/prof_r2f python tools/ncu_target.py > gpurun_out/ncu_r2f.log 2>&1;;
  att)   ncu $N -k 'regex:gemm_tc_kernel<\(int\)4, \(int\)128>' -s 1 -c 1 -o gpurun_out/prof_att python tools/ncu_target.py > gpurun_out/ncu_att.log 2>&1;;
  pool)  ncu $N -k 'regex:gemm_tc_kernel<\(int\)2, \(int\)256>' -s 1 -c 1 -o gpurun_out/prof_pool python tools/ncu_target.py > gpurun_out/ncu_pool.log 2>&1;;
  fbank) ncu $N -k 'regex:fbank_frames' -s 1 -c 1 -o gpurun_out/prof_fbank python tools/ncu_target.py > gpurun_out/ncu_fbank.log 2>&1;;
