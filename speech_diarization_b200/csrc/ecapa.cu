@@ -65,6 +65,7 @@ struct Program {     // launch parameters for one (B, T) shape
   GemmParams* chain_dev = nullptr;  // device copy of [3][9]: tdnn1, 7 x Res2Net, tdnn2 per block
   Res2Params r2[3];                 // the 7 Res2Net convs of a block as one launch (res2net_fused.cuh)
   bool r2_ok = false;               // shape fits the fused kernel (16 <= T, T + 2*dil <= 168)
+  bool colsum_ok = false;           // Tp >= 128: SE / ASP time statistics come out of the GEMM write-outs
   cudaGraphExec_t graph = nullptr;  // captured trunk (block0 .. FC) for this shape
   int graph_launches = 0;
   int runs = 0;
@@ -88,6 +89,7 @@ struct SdEcapaPlan {
   __half *feats = nullptr, *x0 = nullptr, *cat = nullptr, *u = nullptr, *v = nullptr, *w = nullptr;
   __half *s[2] = {nullptr, nullptr}, *h = nullptr, *attn = nullptr;
   float *raw = nullptr, *se_mean = nullptr, *se_hid = nullptr, *se_scale = nullptr, *stats = nullptr;
+  float *cs_se = nullptr, *cs_mfa = nullptr, *cq_mfa = nullptr;  // per (m block, window slot) column sums from the GEMM write-outs
   float *uttbias = nullptr, *pooled = nullptr, *emb_tmp = nullptr, *ctx_part = nullptr;
   __half *stats_h = nullptr, *pooled_h = nullptr;
   std::map<std::pair<int, int>, Program> programs;
@@ -103,6 +105,7 @@ struct SdEcapaPlan {
   bool use_mc = false;
   bool use_2sm = true;     // SD_ECAPA_2SM=0: 256-wide GEMMs with cta_group::1 instead of CTA pairs
   bool use_r2fused = true; // SD_ECAPA_R2FUSED=0: Res2Net chain as 7 launches per block instead of one
+  bool use_colsum = true;  // SD_ECAPA_COLSUM=0: separate passes over the activations for the SE mean and ASP mean/std
   bool use_conv3 = true;   // SD_ECAPA_CONV3=0: Res2Net convs through the generic tap-per-k-iteration path
   bool use_graph = true;   // SD_ECAPA_GRAPH=0 disables CUDA-graph replay of the trunk
   cudaStream_t cap_stream = nullptr;
@@ -300,9 +303,15 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     }
     SD_TRY(setup_tdnn_gemm(pr.tdnn2[b], p->v, R, C1, C1, bw.tdnn2, C1, C1, 256, C1, 1, 1, 0, pr,
                            p->w, C1, 0, 0, p->use_mc || p->use_2sm));
+    pr.colsum_ok = p->use_colsum && pr.Tp >= 128;
+    if (pr.colsum_ok) pr.tdnn2[b].epi.colsum = p->cs_se;
   }
   SD_TRY(setup_tdnn_gemm(pr.mfa, p->cat, R, C3, C3, p->wmfa, C3, C3, 256, C3, 1, 1, 0, pr, p->h, C3,
                          0, 0, p->use_mc || p->use_2sm));
+  if (pr.colsum_ok) {
+    pr.mfa.epi.colsum = p->cs_mfa;
+    pr.mfa.epi.colsq = p->cq_mfa;
+  }
   SD_TRY(setup_tdnn_gemm(pr.att, p->h, R, C3, C3, p->watt, ATT, C3, 128, C3, 1, 1, 0, pr, p->attn,
                          ATT, 0, 0));
   pr.att.epi.utt_bias = p->uttbias;
@@ -515,11 +524,15 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
       SD_TRY(launch_big(p, pr.tdnn2[b], st));
     }
     mark(p, st);
-    time_mean_kernel<<<dim3(C1 / 256, B), 128, 0, st>>>(p->w, C1, Tp, T, HALO, C1, p->se_mean);
-    se_hidden_kernel<<<dim3((B + 3) / 4, SE / 32), 256, 4 * C1 * sizeof(float), st>>>(
+    if (pr.colsum_ok)
+      colstats_finish_kernel<<<dim3(C1 / 256, B), 256, 0, st>>>(p->cs_se, nullptr, p->blk[b].tdnn2.shift, C1, Tp, T,
+                                                               pr.tdnn2[b].num_m_blocks, p->se_mean, C1, nullptr, nullptr);
+    else
+      time_mean_kernel<<<dim3(C1 / 256, B), 128, 0, st>>>(p->w, C1, Tp, T, HALO, C1, p->se_mean);
+    se_hidden_kernel<<<dim3((B + SE_U - 1) / SE_U, SE / 32), 256, SE_U * C1 * sizeof(float), st>>>(
         p->se_mean, p->blk[b].se_w1, p->blk[b].se_b1, B, C1, SE, p->se_hid);
-    se_scale_kernel<<<dim3((B + 3) / 4, C1 / 256), 256, 0, st>>>(p->se_hid, p->blk[b].se_w2t, p->blk[b].se_b2, B,
-                                                                  C1, SE, p->se_scale);
+    se_scale_kernel<<<dim3((B + SE_U - 1) / SE_U, C1 / 256), 256, 0, st>>>(p->se_hid, p->blk[b].se_w2t,
+                                                                          p->blk[b].se_b2, B, C1, SE, p->se_scale);
     const long vecs = R * (C1 / 8);
     const int grid = (int)((vecs + 255) / 256 < 148L * 16 ? (vecs + 255) / 256 : 148L * 16);
     se_apply_kernel<<<grid, 256, 0, st>>>(p->w, C1, p->se_scale, in, ld_in, p->cat + (size_t)b * C1, C3, R,
@@ -530,7 +543,11 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
   mark(p, st);
   SD_TRY(launch_big(p, pr.mfa, st));
   mark(p, st);
-  time_mean_std_kernel<<<dim3(C3 / 256, B), 128, 0, st>>>(p->h, C3, Tp, T, HALO, C3, p->stats, p->stats_h);
+  if (pr.colsum_ok)
+    colstats_finish_kernel<<<dim3(C3 / 256, B), 256, 0, st>>>(p->cs_mfa, p->cq_mfa, p->wmfa.shift, C3, Tp, T,
+                                                             pr.mfa.num_m_blocks, p->stats, 2 * C3, p->stats + C3, p->stats_h);
+  else
+    time_mean_std_kernel<<<dim3(C3 / 256, B), 128, 0, st>>>(p->h, C3, Tp, T, HALO, C3, p->stats, p->stats_h);
   SD_CUDA_OK(cudaGetLastError());
   count_launch(1);
   // context bias: W_mean . mean + W_std . std  (the 2/3 of asp.tdnn that is constant over time)
@@ -612,6 +629,7 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   if (const char* e = getenv("SD_ECAPA_GRAPH")) p->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_CONV3")) p->use_conv3 = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_R2FUSED")) p->use_r2fused = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_COLSUM")) p->use_colsum = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_MC")) p->use_mc = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_2SM")) p->use_2sm = atoi(e) != 0;
   if (p->use_chain) p->use_mc = p->use_2sm = false;  // the cooperative chain uses the plain kernels
@@ -704,6 +722,12 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
     SD_TRY(dev_alloc(p, (void**)&p->se_mean, MB * C1 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->se_scale, MB * C1 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->se_hid, MB * SE * 4, true));
+    {
+      const size_t mblocks = (size_t)(p->max_rows + BM - 1) / BM + 1;
+      SD_TRY(dev_alloc(p, (void**)&p->cs_se, mblocks * 2 * C1 * 4, true));
+      SD_TRY(dev_alloc(p, (void**)&p->cs_mfa, mblocks * 2 * C3 * 4, true));
+      SD_TRY(dev_alloc(p, (void**)&p->cq_mfa, mblocks * 2 * C3 * 4, true));
+    }
     SD_TRY(dev_alloc(p, (void**)&p->stats, MB * 2 * C3 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->uttbias, MB * ATT * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->pooled, MB * 2 * C3 * 4, true));

@@ -19,7 +19,9 @@ namespace sd {
 __global__ void __launch_bounds__(128)
 time_mean_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H, int C,
                  float* __restrict__ mean_out /*[B, C]*/) {
-  const int b = blockIdx.y;
+  // utterances last to first: the producer GEMM wrote them first to last, so the most recently written
+  // (still L2-resident) rows are read first instead of being evicted by this kernel's own misses
+  const int b = gridDim.y - 1 - blockIdx.y;
   const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
   if (c >= C) return;
   const __half2* p = reinterpret_cast<const __half2*>(x + (static_cast<size_t>(b) * Tp + H) * ld + c);
@@ -100,69 +102,122 @@ time_mean_std_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H,
   }
 }
 
+// Finishes the column statistics the GEMM write-out accumulated per (m block, window slot)
+// (EpiParams::colsum): window b spans m blocks (b*Tp)/128 .. (b*Tp + Tp - 1)/128; its slot in block m is
+// b - (m*128)/Tp.  mean = k + S/T, var = (Q - S^2/T)/T (shift-invariant), std = sqrt(max(var, 1e-12)).
+// grid (C/256, B), block 256.  std_out / out_h may be null; out_h gets [mean | std] as f16 when std is wanted.
+__global__ void __launch_bounds__(256)
+colstats_finish_kernel(const float* __restrict__ colsum, const float* __restrict__ colsq,
+                       const float* __restrict__ shift, int C, int Tp, int T, int num_m_blocks,
+                       float* __restrict__ mean_out, int ld_out, float* __restrict__ std_out,
+                       __half* __restrict__ out_h) {
+  const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  const int m_lo = (b * Tp) / 128;
+  const int m_hi = min((b * Tp + Tp - 1) / 128, num_m_blocks - 1);
+  float S = 0.f, Q = 0.f;
+  for (int m = m_lo; m <= m_hi; ++m) {
+    const int slot = b - (m * 128) / Tp;
+    const size_t o = (static_cast<size_t>(m) * 2 + slot) * C + c;
+    S += colsum[o];
+    if (colsq != nullptr) Q += colsq[o];
+  }
+  const float k = shift != nullptr ? __half2float(__float2half_rn(shift[c])) : 0.f;
+  const float inv = 1.0f / static_cast<float>(T);
+  const float mean = k + S * inv;
+  mean_out[static_cast<size_t>(b) * ld_out + c] = mean;
+  if (std_out != nullptr) {
+    const float sd = sqrtf(fmaxf((Q - S * S * inv) * inv, 1e-12f));
+    std_out[static_cast<size_t>(b) * ld_out + c] = sd;
+    if (out_h != nullptr) {
+      out_h[static_cast<size_t>(b) * ld_out + c] = __float2half_rn(mean);
+      out_h[static_cast<size_t>(b) * ld_out + C + c] = __float2half_rn(sd);
+    }
+  }
+}
+
 // SE excitation, layer 1: hid[b, j] = relu(W1[j, :] . mean[b, :] + b1[j]).   W1 [S][C] row-major.
-// One CTA = 4 utterances (weights read from L2 once per 4) x 32 hidden units (4 per warp).
-// grid (ceil(B/4), S/32), block 256, dynamic smem 4*C floats.
+// One CTA = SE_U utterances x 32 hidden units (4 per warp).  (SE_U = 16 and a tcgen05 version of these two
+// layers were measured: neither beats this — both kernels sit at their launch / latency floor.)
+// grid (ceil(B/SE_U), S/32), block 256, dynamic smem SE_U*C floats.
+constexpr int SE_U = 4;
 __global__ void __launch_bounds__(256)
 se_hidden_kernel(const float* __restrict__ mean, const float* __restrict__ W1,
                  const float* __restrict__ b1, int B, int C, int S, float* __restrict__ hid) {
-  extern __shared__ float sm[];  // [4][C]
-  const int b0 = blockIdx.x * 4, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nb = min(4, B - b0);
-  for (int i = tid; i < 4 * C; i += 256) {
+  extern __shared__ float sm[];  // [SE_U][C]
+  const int b0 = blockIdx.x * SE_U, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = min(SE_U, B - b0);
+  for (int i = tid * 4; i < SE_U * C; i += 256 * 4) {
     const int u = i / C;
-    sm[i] = u < nb ? mean[static_cast<size_t>(b0 + u) * C + (i - u * C)] : 0.f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u < nb) v = *reinterpret_cast<const float4*>(mean + static_cast<size_t>(b0 + u) * C + (i - u * C));
+    *reinterpret_cast<float4*>(sm + i) = v;
   }
   __syncthreads();
-#pragma unroll
+#pragma unroll 1
   for (int jj = 0; jj < 4; ++jj) {
     const int j = blockIdx.y * 32 + warp * 4 + jj;
     if (j >= S) break;
     const float4* w = reinterpret_cast<const float4*>(W1 + static_cast<size_t>(j) * C);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
+    float acc[SE_U];
+#pragma unroll
+    for (int u = 0; u < SE_U; ++u) acc[u] = 0.f;
+#pragma unroll 2
     for (int i = lane; i < C / 4; i += 32) {
       const float4 wv = __ldg(w + i);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < SE_U; ++u) {
         const float4 mv = *reinterpret_cast<const float4*>(sm + u * C + 4 * i);
         acc[u] += wv.x * mv.x + wv.y * mv.y + wv.z * mv.z + wv.w * mv.w;
       }
     }
+    const float bj = b1[j];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < SE_U; ++u) {
       const float a = warp_sum(acc[u]);
-      if (lane == 0 && u < nb) hid[static_cast<size_t>(b0 + u) * S + j] = fmaxf(a + b1[j], 0.f);
+      if (lane == 0 && u < nb) hid[static_cast<size_t>(b0 + u) * S + j] = fmaxf(a + bj, 0.f);
     }
   }
 }
 
 // SE excitation, layer 2: scale[b, c] = sigmoid(W2[c, :] . hid[b, :] + b2[c]).   W2t [S][C] (transposed
 // conv2 weight, so consecutive threads read consecutive addresses).
-// grid (ceil(B/4), C/256), block 256.  S <= 128.
+// grid (ceil(B/SE_U), C/256), block 256.  S <= 128, S % 4 == 0.
 __global__ void __launch_bounds__(256)
 se_scale_kernel(const float* __restrict__ hid, const float* __restrict__ W2t,
                 const float* __restrict__ b2, int B, int C, int S, float* __restrict__ scale) {
-  __shared__ float h[4 * 128];
-  const int b0 = blockIdx.x * 4, tid = threadIdx.x;
-  const int nb = min(4, B - b0);
-  for (int i = tid; i < 4 * S; i += 256) {
+  __shared__ __align__(16) float h[SE_U * 128];
+  const int b0 = blockIdx.x * SE_U, tid = threadIdx.x;
+  const int nb = min(SE_U, B - b0);
+  for (int i = tid; i < SE_U * S; i += 256) {
     const int u = i / S;
     h[i] = u < nb ? hid[static_cast<size_t>(b0 + u) * S + (i - u * S)] : 0.f;
   }
   __syncthreads();
   const int c = blockIdx.y * 256 + tid;
   if (c >= C) return;
-  float acc[4];
+  float acc[SE_U];
+  const float bc = b2[c];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) acc[u] = b2[c];
-#pragma unroll 16
-  for (int j = 0; j < S; ++j) {
-    const float wv = __ldg(W2t + static_cast<size_t>(j) * C + c);
+  for (int u = 0; u < SE_U; ++u) acc[u] = bc;
+#pragma unroll 2
+  for (int j = 0; j < S; j += 4) {
+    const float w0 = __ldg(W2t + static_cast<size_t>(j) * C + c);
+    const float w1 = __ldg(W2t + static_cast<size_t>(j + 1) * C + c);
+    const float w2 = __ldg(W2t + static_cast<size_t>(j + 2) * C + c);
+    const float w3 = __ldg(W2t + static_cast<size_t>(j + 3) * C + c);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = fmaf(h[u * S + j], wv, acc[u]);
+    for (int u = 0; u < SE_U; ++u) {
+      const float4 hv = *reinterpret_cast<const float4*>(h + u * S + j);
+      acc[u] = fmaf(hv.x, w0, acc[u]);
+      acc[u] = fmaf(hv.y, w1, acc[u]);
+      acc[u] = fmaf(hv.z, w2, acc[u]);
+      acc[u] = fmaf(hv.w, w3, acc[u]);
+    }
   }
-  for (int u = 0; u < nb; ++u) scale[static_cast<size_t>(b0 + u) * C + c] = 1.0f / (1.0f + __expf(-acc[u]));
+#pragma unroll
+  for (int u = 0; u < SE_U; ++u)
+    if (u < nb) scale[static_cast<size_t>(b0 + u) * C + c] = 1.0f / (1.0f + __expf(-acc[u]));
 }
 
 // out[r, c] = w[r, c] * scale[b(r), c] + res[r, c]  over ALL rows (halo rows included, so the

@@ -103,6 +103,12 @@ struct EpiParams {
   int C;
   // EPI_AFF
   double* out_f64;  // optional second copy as f64 (AHC working matrix), same ld
+  // EPI_TDNN, n_tile = 256, Tp >= 128, no EF_REFLECT: per-window column statistics fused into the write-out
+  // (tdnn2 -> SE squeeze mean, MFA -> ASP mean/std).  colsum[(m_blk*2 + slot)*N_cols + c] = sum over the
+  // tile's interior frames of window (m_blk*128/Tp + slot) of x - k[c]; colsq the same of (x - k[c])^2;
+  // k[c] = f16(shift[c]), the value a channel takes wherever its ReLU is off.
+  float* colsum;
+  float* colsq;
 };
 
 struct alignas(64) GemmParams {
@@ -145,7 +151,7 @@ struct GemmCfg {
   static constexpr bool STAGED_OUT = (epi_is_tdnn(EPI) || EPI == EPI_ATT || EPI == EPI_AFF);
   static constexpr int OUT_STAGE_BYTES = STAGED_OUT ? 65536 : 0;
   static constexpr int STAGES = CONV ? 3 : (EPI == EPI_POOL) ? 2 : (STAGED_OUT ? ((MAX_BN == 256) ? 3 : 4) : ((MAX_BN == 256) ? 4 : 6));
-  static constexpr int EPI_SMEM_FLOATS = 3 * 256;     // EPI_TDNN: bias/scale/shift of one n block
+  static constexpr int EPI_SMEM_FLOATS = 3 * 256 + 1024;  // EPI_TDNN: bias/scale/shift of one n block + colsum exchange
   // EPI_POOL: two buffers of [2 chunks][n_tile rows][128 B] (n_tile <= 256 -> 64 KB each)
   // EPI_POOL additionally needs 2 KB to combine the two column halves of the softmax statistics
   static constexpr int EPI_REGION_BYTES = (EPI == EPI_POOL) ? 2 * 2 * MAX_BN * 128 + 2048 : EPI_SMEM_FLOATS * 4;
@@ -343,6 +349,112 @@ __device__ __forceinline__ void tdnn_writeout(const GemmParams& P, int m_blk, in
         *reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r) * E.ld_sum + col) = sv;
         if (r2 >= 0) *reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r2) * E.ld_sum + col) = sv;
         if (r3 >= 0) *reinterpret_cast<uint4*>(E.sum_out + static_cast<size_t>(r3) * E.ld_sum + col) = sv;
+      }
+    }
+  }
+}
+
+// Write-out + per-window column statistics for 256-wide tiles (see EpiParams::colsum).  Warp `we` owns the
+// 64-column chunk we>>1 and rows (we&1)*64 .. +63: a store instruction still covers four complete 128-byte
+// lines, and a column's partial sum lives in one warp (shuffle over its 4 row lanes).  The two warps of a
+// chunk combine through `part` (shared memory) in a fixed order, so the result is deterministic.
+__device__ __forceinline__ void tdnn_writeout_colsum(const GemmParams& P, int m_blk, int n_blk,
+                                                     const uint8_t* stage_out, float* part, int et) {
+  const EpiParams& E = P.epi;
+  const int we = et >> 5, lane = et & 31;
+  const int j = we >> 1, hrow = (we & 1) * 64;
+  const int sub = lane & 7, rlo = lane >> 3;
+  const int col = n_blk * P.n_tile + j * 64 + sub * 8;  // first of this thread's 8 channels
+  const bool want_sq = E.colsq != nullptr;
+  float k[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    k[e] = (E.shift != nullptr && col + e < E.N_cols) ? __half2float(__float2half_rn(__ldg(E.shift + col + e))) : 0.f;
+  const int row0 = m_blk * BM;
+  const int b0 = row0 / E.Tp;
+  const int rb = (b0 + 1) * E.Tp - row0;      // tile-relative first row of window b0 + 1
+  const int tbase0 = row0 - b0 * E.Tp - E.H;  // frame index of tile row 0 inside window b0
+  float s0[8], s1[8], q0[8], q1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = q0[e] = q1[e] = 0.f;
+  __half* out = reinterpret_cast<__half*>(E.out);
+  const uint8_t* sbase = stage_out + j * 16384;
+#pragma unroll 4
+  for (int pass = 0; pass < 16; ++pass) {
+    const int rl = hrow + pass * 4 + rlo;
+    const int r = row0 + rl;
+    if (r >= E.M_rows) continue;
+    const uint4 val = *reinterpret_cast<const uint4*>(sbase + rl * 128 + ((sub ^ (rl & 7)) << 4));
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * E.ld_out + E.out_col_off + col) = val;
+    const bool second = rl >= rb;
+    const int t = second ? rl - rb - E.H : rl + tbase0;
+    if (t < 0 || t >= E.T) continue;
+    const __half2* vh = reinterpret_cast<const __half2*>(&val);
+    float d[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(vh[e]);
+      d[2 * e] = f.x - k[2 * e];
+      d[2 * e + 1] = f.y - k[2 * e + 1];
+    }
+    if (!second) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s0[e] += d[e];
+        if (want_sq) q0[e] = fmaf(d[e], d[e], q0[e]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s1[e] += d[e];
+        if (want_sq) q1[e] = fmaf(d[e], d[e], q1[e]);
+      }
+    }
+  }
+  // over the 4 row lanes of the warp
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 8);
+    s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 16);
+    s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
+    s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+    if (want_sq) {
+      q0[e] += __shfl_xor_sync(0xffffffffu, q0[e], 8);
+      q0[e] += __shfl_xor_sync(0xffffffffu, q0[e], 16);
+      q1[e] += __shfl_xor_sync(0xffffffffu, q1[e], 8);
+      q1[e] += __shfl_xor_sync(0xffffffffu, q1[e], 16);
+    }
+  }
+  // part: [quantity s|q][chunk j][slot][64 columns]
+  float* ps = part + (j * 2) * 64 + sub * 8;
+  float* pq = ps + 512;
+  if ((we & 1) && rlo == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      ps[e] = s0[e];
+      ps[64 + e] = s1[e];
+      if (want_sq) {
+        pq[e] = q0[e];
+        pq[64 + e] = q1[e];
+      }
+    }
+  }
+  epi_named_barrier();
+  if (!(we & 1) && rlo == 0 && col < E.N_cols) {
+    float* g0 = E.colsum + (static_cast<size_t>(m_blk) * 2) * E.N_cols + col;
+    float* g1 = g0 + E.N_cols;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      g0[e] = s0[e] + ps[e];
+      g1[e] = s1[e] + ps[64 + e];
+    }
+    if (want_sq) {
+      float* h0 = E.colsq + (static_cast<size_t>(m_blk) * 2) * E.N_cols + col;
+      float* h1 = h0 + E.N_cols;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        h0[e] = q0[e] + pq[e];
+        h1[e] = q1[e] + pq[64 + e];
       }
     }
   }
@@ -827,7 +939,8 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       if (++ps.as == acc_stages) { ps.as = 0; ps.aphase ^= 1; }
       if (epi_is_tdnn(EPI) || EPI == EPI_ATT) {
         epi_named_barrier();   // staging tile complete
-        tdnn_writeout(P, m_blk, n_blk, stage_out, et);
+        if (epi_is_tdnn(EPI) && P.epi.colsum != nullptr) tdnn_writeout_colsum(P, m_blk, n_blk, stage_out, epi_sp + 768, et);
+        else tdnn_writeout(P, m_blk, n_blk, stage_out, et);
       }
       if (EPI == EPI_AFF) {
         epi_named_barrier();
@@ -876,7 +989,7 @@ struct Cfg2sm {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
   static constexpr int STAGES = 4;
   static constexpr int OUT_STAGE_BYTES = 65536;
-  static constexpr int EPI_BYTES = 3 * 256 * 4;
+  static constexpr int EPI_BYTES = (3 * 256 + 1024) * 4;   // per-column constants + colsum exchange
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + EPI_BYTES + 256;
 };
 
@@ -1005,7 +1118,8 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
       if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);  // this CTA's share of the accumulator is drained
       if (++as == 2) { as = 0; aphase ^= 1; }
       epi_named_barrier();  // staging tile complete
-      tdnn_writeout(P, m_blk, n_blk, stage_out, et);
+      if (P.epi.colsum != nullptr) tdnn_writeout_colsum(P, m_blk, n_blk, stage_out, epi_sp + 768, et);
+      else tdnn_writeout(P, m_blk, n_blk, stage_out, et);
     }
   }
 

@@ -120,7 +120,8 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
       int slot = 0;
       uint32_t ph = 0;
       int n = 0;  // convolutions this CTA has started (all roles count the same sequence)
-      for (int w = blockIdx.x; w < P.B; w += gridDim.x) {
+      for (int ws = blockIdx.x; ws < P.B; ws += gridDim.x) {
+        const int w = P.B - 1 - ws;  // last windows first: tdnn1 wrote them last, so they are still in L2
         if (n > 0) mbar_wait(t_full, (n - 1) & 1);  // the previous window's last conv is done reading A
         mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(2 * RA * 128));
         const int row0 = w * Tp + H - d;
@@ -144,7 +145,7 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
       uint32_t ph = 0;
       int n = 0, wi = 0;
       const uint32_t a_addr0 = smem_u32(abuf);
-      for (int w = blockIdx.x; w < P.B; w += gridDim.x, ++wi) {
+      for (int ws = blockIdx.x; ws < P.B; ws += gridDim.x, ++wi) {
         for (int i = 0; i < R2_CONVS; ++i, ++n) {
           if (i == 0) mbar_wait(a_full, wi & 1);
           if (n > 0) mbar_wait(acc_free, (n - 1) & 1);  // TMEM drained, next input written (i > 0)
@@ -193,9 +194,10 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
     const int my_mt = (quarter * 32 < T ? 1 : 0) + (128 + quarter * 32 < T ? 1 : 0);
     const int nk = 2 * my_mt;
     int n = 0;
-    for (int w = blockIdx.x; w < P.B; w += gridDim.x) {
+    for (int ws = blockIdx.x; ws < P.B; ws += gridDim.x) {
+      const int w = P.B - 1 - ws;
       const size_t wrow = static_cast<size_t>(w) * Tp;
-      const bool more_windows = w + static_cast<int>(gridDim.x) < P.B;
+      const bool more_windows = ws + static_cast<int>(gridDim.x) < P.B;
       for (int i = 0; i < R2_CONVS; ++i, ++n) {
         const float* const cs = consts + (n & 1) * 384;
         // the next conv's constants go to the other buffer right away: its last readers finished a whole

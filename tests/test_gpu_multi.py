@@ -52,7 +52,9 @@ def test_two_gpu_pipeline_matches_single_gpu():
     n = sharded.window_count(y.numel(), 24000, 12000)
     ref = enc.embed_device(y, 12000, n, 24000, l2_normalize=True).cpu().numpy()
     for rank, emb, labels, segs, rng in res:
-        np.testing.assert_array_equal(emb, ref)            # same kernels, same inputs -> bit-identical
+        # same kernels, same inputs; a shard places a window at a different batch offset, which changes the f32
+        # association of the fused SE/ASP time statistics (see test_batch_properties_full_size) -> ~1e-5 on unit-norm embeddings
+        np.testing.assert_allclose(emb, ref, rtol=0, atol=1e-4)
         assert rng == sharded.shard_range(n, rank, 2)
     np.testing.assert_array_equal(res[0][2], res[1][2])
     single = clustering.cluster_embeddings_device(torch.from_numpy(ref).cuda(), 0.68).cpu().numpy()
