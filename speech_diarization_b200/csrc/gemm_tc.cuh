@@ -478,6 +478,71 @@ struct PoolState {
   float mx = -INFINITY, se = 0.f, s1 = 0.f, s2 = 0.f;
 };
 
+// Register-resident form of the two softmax passes for utterances of <= NCH*32 padded frames handled in
+// one time chunk: the warp's NCH 16-column runs of logits are read from TMEM once (all loads in flight
+// together, one wait), frames outside [0, T) are set to -inf so both passes are branch-free, and the
+// three running sums use two independent accumulators each.  The generic path below (two TMEM reads,
+// one wait per 16 columns, per-element edge tests) was issue- and latency-bound: 17 instructions and
+// ~70 cycles per element per warp in ncu (profiles/r01_ncu_head.txt).
+template <int NCH>
+__device__ __forceinline__ void pool_chunks_regs(const GemmParams& P, uint32_t tbase, int half,
+                                                 const uint8_t* hchunk, int c16, float g, PoolState& st) {
+  const EpiParams& E = P.epi;
+  const float LOG2E = 1.4426950408889634f;
+  uint32_t v[NCH][16];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c0 = (2 * i + half) * 16;
+    if (c0 < P.n_tile) tmem_ld16(tbase + c0, v[i]);
+  }
+  tmem_ld_wait();
+  float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int t0 = (2 * i + half) * 16 - E.H;  // frame index of the run's first column
+    if (!(t0 >= 0 && t0 + 16 <= E.T)) {        // run touches the halo / padding (warp-uniform)
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (t0 + j < 0 || t0 + j >= E.T) v[i][j] = 0xff800000u;  // -inf: ignored by max, exp2 -> 0
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cm[j & 3] = fmaxf(cm[j & 3], __uint_as_float(v[i][j]));
+  }
+  const float mx = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
+  const float mxs = (mx == -INFINITY) ? 0.f : mx * LOG2E;
+  float se[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c0 = (2 * i + half) * 16;
+    const int t0 = c0 - E.H;
+    if (c0 < P.n_tile) {
+      float xv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int p = c0 + j;
+        xv[j] = __half2float(*reinterpret_cast<const __half*>(hchunk + p * 128 + ((c16 ^ (p & 7)) << 4))) - g;
+      }
+      if (!(t0 >= 0 && t0 + 16 <= E.T)) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (t0 + j < 0 || t0 + j >= E.T) xv[j] = 0.f;  // weight is exactly 0; keep 0 * garbage out
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float e = ex2_approx(fmaf(__uint_as_float(v[i][j]), LOG2E, -mxs));
+        se[j & 1] += e;
+        const float ex = e * xv[j];
+        s1[j & 1] += ex;
+        s2[j & 1] = fmaf(ex, xv[j], s2[j & 1]);
+      }
+    }
+  }
+  st.mx = mx;
+  st.se = se[0] + se[1];
+  st.s1 = s1[0] + s1[1];
+  st.s2 = s2[0] + s2[1];
+}
+
 __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, int n_blk, int sub,
                                               uint32_t tmem_acc, int quarter, int half, int lane,
                                               const uint8_t* hbuf, float4* xchg, PoolState& st) {
@@ -489,67 +554,73 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
   const bool chv = ch < E.C;
   const float LOG2E = 1.4426950408889634f;
   const int f0 = sub * P.n_tile - E.H;  // frame index of this chunk's column 0
-  // this warp's share of the frames: 16-column chunks  half, half+2, ...
-  // pass 1: max over this chunk's interior frames
-  float cm = -INFINITY;
-  for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
-    uint32_t v[16];
-    tmem_ld16(tbase + c0, v);
-    tmem_ld_wait();
-    if (f0 + c0 >= 0 && f0 + c0 + 16 <= E.T) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int t = f0 + c0 + j;
-        if (t >= 0 && t < E.T) cm = fmaxf(cm, __uint_as_float(v[j]));
-      }
-    }
-  }
-  // online softmax: rescale what earlier chunks accumulated to the new running maximum
-  if (cm > st.mx) {
-    const float f = (st.mx == -INFINITY) ? 0.f : ex2_approx((st.mx - cm) * LOG2E);
-    st.se *= f;
-    st.s1 *= f;
-    st.s2 *= f;
-    st.mx = cm;
-  }
-  // pass 2: softmax-weighted first/second moments about the global mean g
   const float g = chv ? E.gmean[static_cast<size_t>(b) * E.ld_gmean + ch] : 0.f;
   const uint8_t* hchunk = hbuf + (chl >> 6) * (P.n_tile * 128) + (chl & 7) * 2;
   const int c16 = (chl & 63) >> 3;
-  const float mxs = (st.mx == -INFINITY) ? 0.f : st.mx * LOG2E;  // nothing interior seen yet
-  float se = st.se, s1 = st.s1, s2 = st.s2;
-  for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
-    uint32_t v[16];
-    tmem_ld16(tbase + c0, v);
-    float xv[16];
+  float se, s1, s2;
+  if (P.n_sub == 1 && P.n_tile <= 160) {
+    pool_chunks_regs<5>(P, tbase, half, hchunk, c16, g, st);
+    se = st.se; s1 = st.s1; s2 = st.s2;
+  } else {
+    // this warp's share of the frames: 16-column chunks  half, half+2, ...
+    // pass 1: max over this chunk's interior frames
+    float cm = -INFINITY;
+    for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
+      uint32_t v[16];
+      tmem_ld16(tbase + c0, v);
+      tmem_ld_wait();
+      if (f0 + c0 >= 0 && f0 + c0 + 16 <= E.T) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int p = c0 + j;
-      xv[j] = __half2float(*reinterpret_cast<const __half*>(hchunk + p * 128 + ((c16 ^ (p & 7)) << 4))) - g;
-    }
-    tmem_ld_wait();
-    if (f0 + c0 >= 0 && f0 + c0 + 16 <= E.T) {
+        for (int j = 0; j < 16; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
+      } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float e = ex2_approx(fmaf(__uint_as_float(v[j]), LOG2E, -mxs));
-        se += e;
-        const float ex = e * xv[j];
-        s1 += ex;
-        s2 = fmaf(ex, xv[j], s2);
+        for (int j = 0; j < 16; ++j) {
+          const int t = f0 + c0 + j;
+          if (t >= 0 && t < E.T) cm = fmaxf(cm, __uint_as_float(v[j]));
+        }
       }
-    } else {
+    }
+    // online softmax: rescale what earlier chunks accumulated to the new running maximum
+    if (cm > st.mx) {
+      const float f = (st.mx == -INFINITY) ? 0.f : ex2_approx((st.mx - cm) * LOG2E);
+      st.se *= f;
+      st.s1 *= f;
+      st.s2 *= f;
+      st.mx = cm;
+    }
+    // pass 2: softmax-weighted first/second moments about the global mean g
+    const float mxs = (st.mx == -INFINITY) ? 0.f : st.mx * LOG2E;  // nothing interior seen yet
+    se = st.se; s1 = st.s1; s2 = st.s2;
+    for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
+      uint32_t v[16];
+      tmem_ld16(tbase + c0, v);
+      float xv[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int t = f0 + c0 + j;
-        if (t >= 0 && t < E.T) {
+        const int p = c0 + j;
+        xv[j] = __half2float(*reinterpret_cast<const __half*>(hchunk + p * 128 + ((c16 ^ (p & 7)) << 4))) - g;
+      }
+      tmem_ld_wait();
+      if (f0 + c0 >= 0 && f0 + c0 + 16 <= E.T) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
           const float e = ex2_approx(fmaf(__uint_as_float(v[j]), LOG2E, -mxs));
           se += e;
           const float ex = e * xv[j];
           s1 += ex;
           s2 = fmaf(ex, xv[j], s2);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int t = f0 + c0 + j;
+          if (t >= 0 && t < E.T) {
+            const float e = ex2_approx(fmaf(__uint_as_float(v[j]), LOG2E, -mxs));
+            se += e;
+            const float ex = e * xv[j];
+            s1 += ex;
+            s2 = fmaf(ex, xv[j], s2);
+          }
         }
       }
     }

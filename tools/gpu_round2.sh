@@ -1,0 +1,13 @@
+#!/bin/bash
+# HEAD validation: gpu tests, bench (+reference arm), launch list, ncu full of the fused kernels.
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/pytest_gpu.log
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+tail -c 2500 gpurun_out/bench.json
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; echo "ref rc=$?"
+python tools/ncu_target.py > gpurun_out/ncu_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/ncu_target.py > gpurun_out/ncu_launches.log 2>&1
+echo "launch list rc=$?"
+bash tools/ncu_gemm.sh mfa tdnn2 r2f se pool
