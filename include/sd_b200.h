@@ -182,6 +182,53 @@ int sd_window_argmax(const float* x_dev, const float* cent_dev, int N, int K, in
  * (scd_split_segments, anti_stick_diarize.py:102-104). */
 int sd_adjacent_cosine(const float* x_dev, int N, int D, float* sims_dev, void* stream);
 
+/* ------------------------------------- score post-processing and VAD masks ---
+ * (the small stages either side of the embedding / clustering path.)
+ *
+ * Viterbi decoding of a sticky K-state HMM over per-step scores — viterbi_hmm(scores, alpha)
+ * (diar_diag.py:231-247; call site :393).  scores_dev [T, K] f32 (scores_f64 = 0) or f64 (= 1);
+ * log_stay = f32(log(alpha + 1e-8)), log_move = f32(log((1 - alpha) / (K - 1) + 1e-8)) as the reference
+ * builds logA.  The recursion is the reference's float32 one, operation for operation (one rounded add
+ * per candidate, first maximum wins), so path_dev [T] int32 is identical, ties included.  1 <= K <= 32.
+ * workspace_dev: sd_viterbi_workspace_bytes(T, K) bytes. */
+size_t sd_viterbi_workspace_bytes(int T, int K);
+int sd_viterbi_hmm(const void* scores_dev, int scores_f64, int T, int K, float log_stay, float log_move,
+                   int32_t* path_dev, void* workspace_dev, void* stream);
+
+/* Adaptive symmetric score normalisation — asnorm_scores(query_embs, ref_centers, cohort_embs, topk)
+ * (diar_diag.py:196-208; call site :389 passes the segment embeddings as their own cohort).
+ * q_dev [nq, D], r_dev [nr, D], c_dev [nc, D] f32; out_dev [nq, nr] f32 =
+ * 0.5 * ((raw - mu_q) / sigma_q + (raw - mu_r) / sigma_r) with raw = Qn Rn^T, and mu / sigma (+1e-6) the
+ * mean / population std of each row's min(topk, nc) largest cohort similarities.  Rows are normalised as
+ * x / (||x|| + 1e-9).  Cohort similarities use the split-f16 tensor-core kernel of
+ * sd_cosine_distance_rowblock; statistics are accumulated in f64.  D % 64 == 0, D <= 512.
+ * workspace_dev: sd_asnorm_workspace_bytes(nq, nr, nc, D) bytes. */
+size_t sd_asnorm_workspace_bytes(int nq, int nr, int nc, int D);
+int sd_asnorm_scores(const float* q_dev, const float* r_dev, const float* c_dev, int nq, int nr, int nc,
+                     int D, int topk, float* out_dev, void* workspace_dev, void* stream);
+
+/* hysteresis_binarize(probs, on, off) (vad.py:59-74; diar_diag.py:331): mask[i] = talking after frame i,
+ * where a silent state turns on at p >= on and a talking state turns off at p < off (compared in f64, as
+ * numba does).  probs_dev [n] f32 (probs_f64 = 0) or f64 (= 1); mask_dev [n] u8 (0 / 1).  A parallel scan
+ * over state maps; bit-exact. */
+int sd_hysteresis_u8(const void* probs_dev, int probs_f64, int n, double on, double off,
+                     uint8_t* mask_dev, void* stream);
+
+/* morph_open_close(mask, hop_ms, open_ms, close_ms) (vad.py:77-87): scipy.ndimage binary_opening then
+ * binary_closing with flat structures of open_w / close_w frames (0 = skip), border value 0.
+ * mask_dev, out_dev, tmp_dev: [n] u8; out_dev and tmp_dev must not alias mask_dev.  Bit-exact. */
+int sd_morph_open_close_u8(const uint8_t* mask_dev, int n, int open_w, int close_w, uint8_t* out_dev,
+                           uint8_t* tmp_dev, void* stream);
+
+/* The frame-index part of mask_to_segments (vad.py:90-151): runs of ones, runs shorter than
+ * min_speech_frames dropped, neighbours with a gap <= min_gap_frames merged.  seg_dev receives
+ * [count][2] int32 (start frame, end frame exclusive), capacity n/2 + 1 pairs; count_dev [1] int32.
+ * Padding and the conversion to rounded seconds (vad.py:153-161) stay with the caller.
+ * workspace_dev: sd_mask_segments_workspace_bytes(n) bytes. */
+size_t sd_mask_segments_workspace_bytes(int n);
+int sd_mask_segments_i32(const uint8_t* mask_dev, int n, int min_speech_frames, int min_gap_frames,
+                         int32_t* seg_dev, int32_t* count_dev, void* workspace_dev, void* stream);
+
 /* ------------------------------------------------------------ debug / test ---
  * Raw tensor-core GEMM used by the unit tests of the tcgen05 kernel:
  *   D[m, n] = sum_{j < taps} sum_{k < K} A[m + (j - taps/2) * dil, k] * B[n, j*K + k]

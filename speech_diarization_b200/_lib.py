@@ -45,6 +45,14 @@ SIGNATURES = {
     "sd_centroid_linkage_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sd_window_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sd_adjacent_cosine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sd_viterbi_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "sd_viterbi_hmm": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "sd_asnorm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "sd_asnorm_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "sd_hysteresis_u8": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
+    "sd_morph_open_close_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "sd_mask_segments_workspace_bytes": (c_size_t, [c_int]),
+    "sd_mask_segments_i32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sd_debug_gemm_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

@@ -1,11 +1,14 @@
 """Drop-in for the hot-path pieces of /root/reference/diar_diag.py:
-``cluster_embeddings`` (:213-229, "agglo" branch) and the ``frame_audio`` duplicate (:48-56).
-Whitening / AS-norm / Viterbi / plotting are "next" rows and not built."""
+``cluster_embeddings`` (:213-229, "agglo" branch), the ``frame_audio`` duplicate (:48-56), and the score
+post-processing of its pipeline: ``asnorm_scores`` (:196-208) and ``viterbi_hmm`` (:231-247)
+(SURVEY.md §8f rank 4).  Whitening and plotting are not built."""
 from __future__ import annotations
 
 import numpy as np
+import torch
 
-from . import _lib
+from . import _lib, postproc
+from ._device import require_cuda
 from .clustering import cluster_embeddings_device, to_cuda_embeddings
 
 
@@ -32,3 +35,29 @@ def cluster_embeddings(embs: np.ndarray, method="hdbscan", cos_thr: float = 0.68
     if method == "hdbscan":
         raise NotImplementedError("method='hdbscan' is outside the B200 hot path (SURVEY.md §2 #9-10); use 'agglo'")
     raise ValueError("method 必须是 hdbscan 或 agglo")      # diar_diag.py:228
+
+
+def asnorm_scores(query_embs: np.ndarray, ref_centers: np.ndarray, cohort_embs: np.ndarray,
+                  topk: int = 200) -> np.ndarray:
+    """diar_diag.py:196-208 — adaptive symmetric normalisation of query x centre cosine scores against the
+    top-k cohort similarities of each side.  Computed on the GPU in f32 (cohort similarities on the tensor
+    cores, statistics in f64); the result has the inputs' result dtype."""
+    res_dtype = np.result_type(np.asarray(query_embs).dtype, np.asarray(ref_centers).dtype,
+                               np.asarray(cohort_embs).dtype, np.float32)
+    q, r, c = (to_cuda_embeddings(x) for x in (query_embs, ref_centers, cohort_embs))
+    if q.shape[1] % 64:
+        raise _lib.SdError(f"embedding dimension {q.shape[1]} must be a multiple of 64 (ECAPA: 192)")
+    return postproc.asnorm_device(q, r, c, topk).cpu().numpy().astype(res_dtype, copy=False)
+
+
+def viterbi_hmm(scores: np.ndarray, alpha: float = 0.995) -> np.ndarray:
+    """diar_diag.py:231-247 — most likely state path of a sticky HMM (stay probability alpha) over per-step
+    scores [T, K]; int32 [T].  The float32 recursion of the reference is reproduced exactly on the GPU."""
+    s = np.asarray(scores)
+    T, K = s.shape
+    if s.dtype == np.float16:
+        s = s.astype(np.float32)
+    elif s.dtype not in (np.float32, np.float64):
+        s = s.astype(np.float64)
+    d = torch.from_numpy(np.ascontiguousarray(s)).to(require_cuda())
+    return postproc.viterbi_device(d, alpha).cpu().numpy().astype(np.int32)

@@ -8,6 +8,9 @@ replaced by empty stub modules for the import to succeed.  ``fbank_batch``
 hard-codes 'cuda' (SURVEY defect D6): ``Tensor.cuda`` / ``Module.to('cuda')`` are
 patched to no-ops so the reference's own torchaudio arithmetic runs on CPU.
 
+post_ref.npz holds outputs of diar_diag.asnorm_scores / viterbi_hmm and of
+vad.hysteresis_binarize / morph_open_close / mask_to_segments, again the reference's own functions.
+
 Run:  python tests/golden/make_golden.py        (needs /root/reference; not run on the GPU box)
 """
 import hashlib
@@ -88,6 +91,66 @@ def synth_embeddings(N, K, sigma, seed, D=192):
     return X, lab
 
 
+def synth_probs(n, seed, dtype):
+    """A speech-probability track: smoothed noise around alternating speech / silence plateaus."""
+    rng = np.random.default_rng(seed)
+    plateau = np.repeat(rng.integers(0, 2, n // 40 + 1), 40)[:n].astype(np.float64)
+    p = 0.15 + 0.7 * plateau + 0.25 * rng.standard_normal(n)
+    p = np.convolve(p, np.ones(3) / 3, mode="same")
+    return np.clip(p, 0.0, 1.0).astype(dtype)
+
+
+def make_post_golden():
+    """diar_diag.asnorm_scores / viterbi_hmm (diar_diag.py:196-208,231-247) and
+    vad.hysteresis_binarize / morph_open_close / mask_to_segments (vad.py:59-163), the reference functions
+    themselves (vad's is the numba-compiled one)."""
+    import vad as ref_vad
+    out = {}
+    # ---- AS-norm: the pipeline's own use (cohort = the segment embeddings, diar_diag.py:389) and a small cohort
+    X, lab = synth_embeddings(300, 5, 0.05, 11)
+    cent = np.stack([X[lab == k].mean(0) for k in range(5)])
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True) + 1e-9
+    out["as_X"], out["as_cent"] = X, cent.astype(np.float32)
+    out["as_self"] = ref_dd.asnorm_scores(X, out["as_cent"], X, topk=min(200, len(X)))
+    Xc, _ = synth_embeddings(50, 3, 0.1, 12)
+    out["as_cohort"] = Xc
+    out["as_small"] = ref_dd.asnorm_scores(X[:70], out["as_cent"], Xc, topk=200)       # topk > cohort size
+    # ---- Viterbi: f32 scores (from AS-norm), f64 scores, tie-heavy integer scores, T = 1, K = 2
+    out["vt_scores_as"] = out["as_self"].astype(np.float32)
+    out["vt_path_as"] = ref_dd.viterbi_hmm(out["vt_scores_as"], alpha=0.995)
+    rng = np.random.default_rng(13)
+    out["vt_scores_f64"] = rng.standard_normal((1000, 3))
+    out["vt_path_f64"] = ref_dd.viterbi_hmm(out["vt_scores_f64"], alpha=0.9)
+    out["vt_scores_ties"] = rng.integers(0, 3, (700, 4)).astype(np.float32)
+    out["vt_path_ties"] = ref_dd.viterbi_hmm(out["vt_scores_ties"], alpha=0.5)
+    out["vt_scores_k2"] = rng.standard_normal((257, 2)).astype(np.float32) * 3
+    out["vt_path_k2"] = ref_dd.viterbi_hmm(out["vt_scores_k2"], alpha=0.995)
+    out["vt_scores_t1"] = rng.standard_normal((1, 6)).astype(np.float32)
+    out["vt_path_t1"] = ref_dd.viterbi_hmm(out["vt_scores_t1"], alpha=0.995)
+    # ---- VAD mask operators
+    for tag, (n, seed, dtype, hop) in {"f32": (5000, 21, np.float32, 10.0), "f64": (3333, 22, np.float64, 32.0),
+                                       "short": (37, 23, np.float32, 10.0)}.items():
+        p = synth_probs(n, seed, dtype)
+        m0 = ref_vad.hysteresis_binarize(p, on=0.6, off=0.4)
+        m1 = ref_vad.morph_open_close(m0, hop, open_ms=80.0, close_ms=40.0)
+        m2 = ref_vad.morph_open_close(m0, hop, open_ms=50.0, close_ms=70.0)       # odd / other widths
+        m3 = ref_vad.morph_open_close(m0, hop, open_ms=0.0, close_ms=100.0)
+        out[f"vad_{tag}_probs"], out[f"vad_{tag}_hop"] = p, hop
+        out[f"vad_{tag}_hyst"], out[f"vad_{tag}_morph"] = m0, m1
+        out[f"vad_{tag}_morph_b"], out[f"vad_{tag}_morph_c"] = m2, m3
+        out[f"vad_{tag}_segs"] = np.array(ref_vad.mask_to_segments(m1, hop), dtype=np.float64).reshape(-1, 2)
+        out[f"vad_{tag}_segs_raw"] = np.array(
+            ref_vad.mask_to_segments(m0, hop, min_speech_ms=60.0, min_gap_ms=45.0, speech_pad_ms=30.0),
+            dtype=np.float64).reshape(-1, 2)
+    out["vad_toggle_hyst"] = ref_vad.hysteresis_binarize(out["vad_f32_probs"], on=0.3, off=0.7)   # on < off
+    z = np.zeros(100, dtype=bool)
+    out["vad_empty_segs"] = np.array(ref_vad.mask_to_segments(z, 10.0), dtype=np.float64).reshape(-1, 2)
+    o = np.ones(100, dtype=bool)
+    out["vad_full_segs"] = np.array(ref_vad.mask_to_segments(o, 10.0), dtype=np.float64).reshape(-1, 2)
+    out["vad_full_morph"] = ref_vad.morph_open_close(o, 10.0)
+    np.savez_compressed(os.path.join(OUT, "post_ref.npz"), **out)
+
+
 def main():
     # ---- a3: fbank_batch (speech_encode.py:10-38), the reference function itself
     for tag, (B, n, seed) in {"short": (3, 4000, 1), "win15": (2, 24000, 2)}.items():
@@ -143,6 +206,7 @@ def main():
         embed_out=embs,
         empty_out_shape=np.array(ref_as.embed_segments(ya, 16000, []).shape),
     )
+    make_post_golden()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             p = os.path.join(OUT, f)

@@ -1,0 +1,129 @@
+"""GPU parity of the score post-processing and VAD-mask operators through the
+reference-facing callables diar_diag.asnorm_scores / viterbi_hmm and vad.hysteresis_binarize /
+morph_open_close / mask_to_segments: against the goldens produced by the reference's own functions and
+against the oracle on seeded inputs.  Integer / boolean results must be identical; AS-norm is floating
+point (f32 on both sides): |delta| <= 2e-4 on z-scores of magnitude up to ~50 (relative 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, synth_emb
+
+pytestmark = pytest.mark.gpu
+
+
+def _po():
+    from oracle import post_oracle
+    return post_oracle
+
+
+# ---------------------------------------------------------------------------------- Viterbi
+@pytest.mark.parametrize("tag,alpha", [("as", 0.995), ("f64", 0.9), ("ties", 0.5), ("k2", 0.995), ("t1", 0.995)])
+def test_viterbi_matches_reference_golden(tag, alpha):
+    from speech_diarization_b200 import diar_diag
+    g = golden("post_ref.npz")
+    path = diar_diag.viterbi_hmm(g[f"vt_scores_{tag}"], alpha=alpha)
+    assert path.dtype == np.int32
+    np.testing.assert_array_equal(path, g[f"vt_path_{tag}"])
+
+
+@pytest.mark.parametrize("T,K,dtype,alpha", [(4097, 8, np.float32, 0.995), (1500, 32, np.float64, 0.8),
+                                              (129, 5, np.float32, 0.3), (2, 3, np.float32, 0.995),
+                                              (20000, 4, np.float32, 0.999)])
+def test_viterbi_matches_oracle(T, K, dtype, alpha):
+    from speech_diarization_b200 import diar_diag
+    rng = np.random.default_rng(T + K)
+    scores = rng.standard_normal((T, K)).astype(dtype)
+    if K == 5:
+        scores = np.round(scores)            # many exact ties
+    np.testing.assert_array_equal(diar_diag.viterbi_hmm(scores, alpha), _po().viterbi_hmm(scores, alpha))
+
+
+def test_viterbi_errors_like_reference():
+    from speech_diarization_b200 import _lib, diar_diag
+    with pytest.raises(ZeroDivisionError):
+        diar_diag.viterbi_hmm(np.zeros((5, 1), np.float32))          # (1 - alpha) / (K - 1)
+    with pytest.raises(IndexError):
+        diar_diag.viterbi_hmm(np.zeros((0, 3), np.float32))          # dp[0] = scores[0]
+    with pytest.raises(_lib.SdError):
+        diar_diag.viterbi_hmm(np.zeros((5, 33), np.float32))         # more than 32 states
+
+
+# ---------------------------------------------------------------------------------- AS-norm
+def test_asnorm_matches_reference_golden():
+    from speech_diarization_b200 import diar_diag
+    g = golden("post_ref.npz")
+    X, cent = g["as_X"], g["as_cent"]
+    got = diar_diag.asnorm_scores(X, cent, X, topk=min(200, len(X)))
+    assert got.dtype == np.float32 and got.shape == (300, 5)
+    assert np.abs(got - g["as_self"]).max() <= 2e-4, np.abs(got - g["as_self"]).max()
+    got = diar_diag.asnorm_scores(X[:70], cent, g["as_cohort"], topk=200)
+    assert np.abs(got - g["as_small"]).max() <= 2e-4
+    # the decision the pipeline takes from the scores (diar_diag.py:393-396) is the reference's
+    np.testing.assert_array_equal(np.argmax(diar_diag.asnorm_scores(X, cent, X, 200), axis=1),
+                                  np.argmax(g["as_self"], axis=1))
+
+
+@pytest.mark.parametrize("nq,nr,nc,topk", [(5000, 8, 5000, 200), (257, 3, 9000, 50), (64, 2, 130, 1),
+                                            (600, 4, 55000, 200)])
+def test_asnorm_matches_oracle(nq, nr, nc, topk):
+    from speech_diarization_b200 import diar_diag
+    X, lab = synth_emb(max(nq, nc), nr, 0.05, nq + nc)
+    Q, C = X[:nq], X[:nc]
+    R = np.stack([X[lab == k].mean(0) for k in range(nr)]).astype(np.float32)
+    got = diar_diag.asnorm_scores(Q, R, C, topk)
+    ref = _po().asnorm_scores(Q, R, C, topk)
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.abs(got - ref).max() <= 2e-5 * scale + 2e-4, (np.abs(got - ref).max(), scale)
+
+
+def test_asnorm_empty_queries():
+    from speech_diarization_b200 import diar_diag
+    X, _ = synth_emb(40, 2, 0.05, 1)
+    assert diar_diag.asnorm_scores(X[:0], X[:2], X, 10).shape == (0, 2)
+
+
+# ---------------------------------------------------------------------------------- VAD mask operators
+@pytest.mark.parametrize("tag", ["f32", "f64", "short"])
+def test_vad_mask_ops_match_reference_golden(tag):
+    from speech_diarization_b200 import vad
+    g = golden("post_ref.npz")
+    p, hop = g[f"vad_{tag}_probs"], float(g[f"vad_{tag}_hop"])
+    m0 = vad.hysteresis_binarize(p, on=0.6, off=0.4)
+    assert m0.dtype == np.bool_
+    np.testing.assert_array_equal(m0, g[f"vad_{tag}_hyst"])
+    np.testing.assert_array_equal(vad.morph_open_close(m0, hop, open_ms=80.0, close_ms=40.0), g[f"vad_{tag}_morph"])
+    np.testing.assert_array_equal(vad.morph_open_close(m0, hop, open_ms=50.0, close_ms=70.0), g[f"vad_{tag}_morph_b"])
+    np.testing.assert_array_equal(vad.morph_open_close(m0, hop, open_ms=0.0, close_ms=100.0), g[f"vad_{tag}_morph_c"])
+    segs = vad.mask_to_segments(g[f"vad_{tag}_morph"], hop)
+    np.testing.assert_array_equal(np.array(segs, dtype=np.float64).reshape(-1, 2), g[f"vad_{tag}_segs"])
+    raw = vad.mask_to_segments(m0, hop, min_speech_ms=60.0, min_gap_ms=45.0, speech_pad_ms=30.0)
+    np.testing.assert_array_equal(np.array(raw, dtype=np.float64).reshape(-1, 2), g[f"vad_{tag}_segs_raw"])
+
+
+def test_vad_mask_ops_edge_cases():
+    from speech_diarization_b200 import vad
+    g = golden("post_ref.npz")
+    np.testing.assert_array_equal(vad.hysteresis_binarize(g["vad_f32_probs"], on=0.3, off=0.7), g["vad_toggle_hyst"])
+    assert vad.mask_to_segments(np.zeros(100, bool), 10.0) == []
+    assert vad.mask_to_segments(np.zeros(0, bool), 10.0) == []
+    full = vad.mask_to_segments(np.ones(100, bool), 10.0)
+    np.testing.assert_array_equal(np.array(full), g["vad_full_segs"])
+    np.testing.assert_array_equal(vad.morph_open_close(np.ones(100, bool), 10.0), g["vad_full_morph"])
+    assert vad.hysteresis_binarize(np.zeros(0, np.float32)).shape == (0,)
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (1023, 1), (1024, 2), (1025, 3), (250_000, 4)])
+def test_vad_mask_ops_match_oracle_at_chunk_boundaries(n, seed):
+    """The scans walk 1024 frames at a time: lengths around the chunk size, and 250k frames (~42 min at 10 ms)."""
+    from speech_diarization_b200 import vad
+    po = _po()
+    rng = np.random.default_rng(seed)
+    p = np.clip(np.convolve(rng.random(n + 8), np.ones(9) / 9, mode="valid")[:n] * 1.6 - 0.3, 0, 1).astype(np.float32)
+    m0 = vad.hysteresis_binarize(p, 0.55, 0.45)
+    np.testing.assert_array_equal(m0, po.hysteresis_binarize(p, 0.55, 0.45))
+    for open_ms, close_ms in ((80.0, 40.0), (30.0, 130.0), (10.0, 0.0)):
+        np.testing.assert_array_equal(vad.morph_open_close(m0, 10.0, open_ms, close_ms),
+                                      po.morph_open_close(m0, 10.0, open_ms, close_ms))
+    for args in ((250.0, 100.0, 80.0), (10.0, 0.0, 0.0), (400.0, 300.0, 200.0)):
+        assert vad.mask_to_segments(m0, 10.0, *args) == po.mask_to_segments(m0, 10.0, *args)

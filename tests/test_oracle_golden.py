@@ -178,3 +178,38 @@ def test_product_fcluster_distance_matches_scipy_with_inversions():
         for t in (0.0, 0.3, 0.7, 1.0, 1.2, 5.0):
             assert co.same_partition(fcluster(Z, t, "distance") - 1, fcluster_distance(Z, t)), (n, t)
     assert (np.diff(Z[:, 2]) < 0).any()
+
+
+# ------------------------------------------------------------------ post-processing oracle
+def test_post_oracle_matches_reference_asnorm_and_viterbi():
+    from oracle import post_oracle as po
+    g = golden("post_ref.npz")
+    X, cent = g["as_X"], g["as_cent"]
+    np.testing.assert_array_equal(po.asnorm_scores(X, cent, X, topk=min(200, len(X))), g["as_self"])
+    np.testing.assert_array_equal(po.asnorm_scores(X[:70], cent, g["as_cohort"], topk=200), g["as_small"])
+    for tag, alpha in (("as", 0.995), ("f64", 0.9), ("ties", 0.5), ("k2", 0.995), ("t1", 0.995)):
+        path = po.viterbi_hmm(g[f"vt_scores_{tag}"], alpha=alpha)
+        assert path.dtype == np.int32
+        np.testing.assert_array_equal(path, g[f"vt_path_{tag}"])
+    assert len(set(g["vt_path_ties"].tolist())) > 1 and len(set(g["vt_path_f64"].tolist())) > 1
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64", "short"])
+def test_post_oracle_matches_reference_vad_mask_ops(tag):
+    from oracle import post_oracle as po
+    g = golden("post_ref.npz")
+    p, hop = g[f"vad_{tag}_probs"], float(g[f"vad_{tag}_hop"])
+    m0 = po.hysteresis_binarize(p, 0.6, 0.4)
+    np.testing.assert_array_equal(m0, g[f"vad_{tag}_hyst"])
+    np.testing.assert_array_equal(po.morph_open_close(m0, hop, 80.0, 40.0), g[f"vad_{tag}_morph"])
+    np.testing.assert_array_equal(po.morph_open_close(m0, hop, 50.0, 70.0), g[f"vad_{tag}_morph_b"])
+    np.testing.assert_array_equal(po.morph_open_close(m0, hop, 0.0, 100.0), g[f"vad_{tag}_morph_c"])
+    segs = np.array(po.mask_to_segments(g[f"vad_{tag}_morph"], hop), dtype=np.float64).reshape(-1, 2)
+    np.testing.assert_array_equal(segs, g[f"vad_{tag}_segs"])
+    raw = np.array(po.mask_to_segments(m0, hop, 60.0, 45.0, 30.0), dtype=np.float64).reshape(-1, 2)
+    np.testing.assert_array_equal(raw, g[f"vad_{tag}_segs_raw"])
+    if tag == "f32":
+        np.testing.assert_array_equal(po.hysteresis_binarize(p, 0.3, 0.7), g["vad_toggle_hyst"])
+        assert len(segs) > 5 and m0.any() and not m0.all()
+        assert po.mask_to_segments(np.zeros(100, bool), 10.0) == []
+        np.testing.assert_array_equal(np.array(po.mask_to_segments(np.ones(100, bool), 10.0)), g["vad_full_segs"])
