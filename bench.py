@@ -197,40 +197,115 @@ def ahc_leg(device, with_cpu: bool) -> dict:
     """BASELINE config 4: cosine affinity + AHC at N = 20 000 (K = 8, sigma = 0.02, cos_thr = 0.68)."""
     from speech_diarization_b200 import clustering
     out = {}
-    for N in (5000, 20000):
-        rng = np.random.default_rng(0)
-        c = rng.standard_normal((8, 192)); c /= np.linalg.norm(c, axis=1, keepdims=True)
-        lab = rng.integers(0, 8, N)
-        X = (c[lab] + 0.02 * rng.standard_normal((N, 192))).astype(np.float32)
-        xd = torch.from_numpy(X).to(device)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        best_aff, best_ahc = 1e9, 1e9
-        for rep in range(4):
-            ev[0].record()
-            dist = clustering.cosine_distance_device(xd)
-            ev[1].record()
-            labels, ncl = clustering.ahc_average_device(dist, 1 - 0.68)
-            ev[2].record()
-            torch.cuda.synchronize()
-            if rep:                              # rep 0 = warm-up
-                best_aff = min(best_aff, ev[0].elapsed_time(ev[1]))
-                best_ahc = min(best_ahc, ev[1].elapsed_time(ev[2]))
-        ok = same_partition(labels.cpu().numpy(), lab)
-        stats = clustering.ahc_last_stats()
-        out[f"n{N}"] = {"affinity_ms": best_aff, "ahc_ms": best_ahc, "clusters": int(ncl.item()),
-                        "labels_match_planted": bool(ok), "rnn_rounds": stats["rounds"], "merges": stats["merges"],
-                        "affinity_frac_of_hbm_roofline": (4.0 * N * N / (best_aff * 1e-3)) / 1e9 / PEAK_HBM,
-                        "ahc_frac_of_hbm_roofline": ((4.0 * N * N + 12.0 * N * (N - 8)) / (best_ahc * 1e-3)) / 1e9 / PEAK_HBM}
-        if with_cpu and N == 5000:
-            from oracle import cluster_oracle
-            t0 = time.perf_counter()
-            ref = cluster_oracle.cluster_embeddings(X, "agglo", 0.68)
-            out[f"n{N}"]["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
-            out[f"n{N}"]["labels_match_cpu"] = bool(same_partition(labels.cpu().numpy(), ref))
-        del dist, labels
-        torch.cuda.empty_cache()
+    for N in (5000, 20000, 50000):
+        try:
+            rng = np.random.default_rng(0)
+            c = rng.standard_normal((8, 192)); c /= np.linalg.norm(c, axis=1, keepdims=True)
+            lab = rng.integers(0, 8, N)
+            X = (c[lab] + 0.02 * rng.standard_normal((N, 192))).astype(np.float32)
+            xd = torch.from_numpy(X).to(device)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            best_aff, best_ahc = 1e9, 1e9
+            dist = labels = None
+            for rep in range(4 if N <= 20000 else 2):
+                dist = labels = None                 # free the previous matrix first: the caching allocator then
+                ev[0].record()                       # reuses its block instead of cudaMalloc-ing 4 N^2 bytes in the timed region
+                dist = clustering.cosine_distance_device(xd)
+                ev[1].record()
+                labels, ncl = clustering.ahc_average_device(dist, 1 - 0.68)
+                ev[2].record()
+                torch.cuda.synchronize()
+                if rep:                              # rep 0 = warm-up
+                    best_aff = min(best_aff, ev[0].elapsed_time(ev[1]))
+                    best_ahc = min(best_ahc, ev[1].elapsed_time(ev[2]))
+            ok = same_partition(labels.cpu().numpy(), lab)
+            stats = clustering.ahc_last_stats()
+            out[f"n{N}"] = {"affinity_ms": best_aff, "ahc_ms": best_ahc, "clusters": int(ncl.item()),
+                            "labels_match_planted": bool(ok), "rnn_rounds": stats["rounds"], "merges": stats["merges"],
+                            "affinity_frac_of_hbm_roofline": (4.0 * N * N / (best_aff * 1e-3)) / 1e9 / PEAK_HBM,
+                            "ahc_frac_of_hbm_roofline": ((4.0 * N * N + 12.0 * N * (N - 8)) / (best_ahc * 1e-3)) / 1e9 / PEAK_HBM}
+            if with_cpu and N == 5000:
+                from oracle import cluster_oracle
+                t0 = time.perf_counter()
+                ref = cluster_oracle.cluster_embeddings(X, "agglo", 0.68)
+                out[f"n{N}"]["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+                out[f"n{N}"]["labels_match_cpu"] = bool(same_partition(labels.cpu().numpy(), ref))
+            del dist, labels
+            torch.cuda.empty_cache()
+        except Exception as e:      # a failed size is reported, not fatal to the bench line
+            out[f"n{N}"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+            torch.cuda.empty_cache()
     out["cpu_note"] = "cpu_ms = sklearn cosine_similarity + AgglomerativeClustering (diar_diag.py:219-226) at N=5000; " \
                       "the same call at N=20000 takes ~35 s on 8 cores (BASELINE.md §2) and is not repeated here"
+    return out
+
+
+def post_leg(device, with_cpu: bool) -> dict:
+    """SURVEY §8f rank 4 at the sizes of BASELINE configs 4 / 5: AS-norm of N = 20 000 segment embeddings against
+    themselves (diar_diag.py:389), Viterbi over the 35 990 windows of the dense pass at the reference's 0.1 s step
+    (K = 4 speakers), and the VAD mask chain over 1 h of 10 ms frames.  CUDA events, device-resident inputs;
+    the oracle port timed beside it on smaller samples where it is slow."""
+    from speech_diarization_b200 import postproc
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=3):
+        best = 1e9
+        for rep in range(reps + 1):
+            ev0.record()
+            r = fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = min(best, ev0.elapsed_time(ev1))
+        return best, r
+
+    rng = np.random.default_rng(0)
+    N, K = 20000, 8
+    c = rng.standard_normal((K, 192)); c /= np.linalg.norm(c, axis=1, keepdims=True)
+    lab = rng.integers(0, K, N)
+    X = (c[lab] + 0.05 * rng.standard_normal((N, 192))).astype(np.float32)
+    xd, cd = torch.from_numpy(X).to(device), torch.from_numpy(c.astype(np.float32)).to(device)
+    ms, sc = timed(lambda: postproc.asnorm_device(xd, cd, xd, 200))
+    out["asnorm_n20000"] = {"ms": ms, "argmax_matches_planted": bool((sc.argmax(1).cpu().numpy() == lab).all())}
+    ms, (wh, sweeps) = timed(lambda: postproc.whiten_l2_device(xd, return_sweeps=True))
+    out["whiten_n20000"] = {"ms": ms, "jacobi_sweeps": int(sweeps)}
+    T = 35990
+    scores = torch.from_numpy((rng.standard_normal((T, 4)) + 2.0 * np.eye(4)[np.repeat(rng.integers(0, 4, T // 50 + 1), 50)[:T]])
+                              .astype(np.float32)).to(device)
+    ms, path = timed(lambda: postproc.viterbi_device(scores, 0.995))
+    out["viterbi_t35990_k4"] = {"ms": ms, "us_per_step": 1e3 * ms / T}
+    n = 360000
+    probs = torch.from_numpy(np.clip(np.convolve(rng.random(n + 8), np.ones(9) / 9, mode="valid")[:n] * 1.6 - 0.3, 0, 1)
+                             .astype(np.float32)).to(device)
+
+    def vad_chain():
+        m = postproc.hysteresis_device(probs, 0.6, 0.4)
+        m = postproc.morph_open_close_device(m, 8, 4)
+        return postproc.mask_segments_device(m, 25, 10)
+    ms, segs = timed(vad_chain)
+    out["vad_mask_chain_1h_10ms"] = {"ms": ms, "segments": int(len(segs)), "note": "hysteresis + open/close + segments, "
+                                     "incl. the D2H read of the segment list"}
+    if with_cpu:
+        from oracle import post_oracle
+        t0 = time.perf_counter(); ref = post_oracle.asnorm_scores(X[:5000], c.astype(np.float32), X[:5000], 200)
+        out["asnorm_n20000"]["cpu_ms_n5000"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter(); wref = post_oracle.whiten_l2(X)
+        out["whiten_n20000"]["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["whiten_n20000"]["max_abs_diff_vs_cpu"] = float(np.abs(wh.cpu().numpy() - wref).max())
+        sp = scores.cpu().numpy()
+        t0 = time.perf_counter(); rp = post_oracle.viterbi_hmm(sp, 0.995)
+        out["viterbi_t35990_k4"]["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["viterbi_t35990_k4"]["path_matches_cpu"] = bool((rp == path.cpu().numpy()).all())
+        pp = probs.cpu().numpy()
+        t0 = time.perf_counter()
+        m = post_oracle.hysteresis_binarize(pp, 0.6, 0.4); m = post_oracle.morph_open_close(m, 10.0, 80.0, 40.0)
+        rs = post_oracle.mask_to_segments(m, 10.0, 250.0, 100.0, 0.0)
+        out["vad_mask_chain_1h_10ms"]["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["vad_mask_chain_1h_10ms"]["cpu_note"] = "oracle port: hysteresis is a pure-Python loop (numba-jitted in the reference)"
+        out["vad_mask_chain_1h_10ms"]["segments_match_cpu"] = bool(
+            len(rs) == len(segs) and all(round(int(a) * 0.01, 3) == x and round(int(b) * 0.01, 3) == y
+                                         for (a, b), (x, y) in zip(segs, rs)))
     return out
 
 
@@ -422,6 +497,7 @@ def main() -> None:
         if world == 1 and not args.no_ahc:
             line["dense_pass"] = dense_pass_leg(enc, audio, device)
             line["ahc"] = ahc_leg(device, with_cpu=not args.no_cpu_baseline)
+            line["post"] = post_leg(device, with_cpu=not args.no_cpu_baseline)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -207,6 +207,16 @@ size_t sd_asnorm_workspace_bytes(int nq, int nr, int nc, int D);
 int sd_asnorm_scores(const float* q_dev, const float* r_dev, const float* c_dev, int nq, int nr, int nc,
                      int D, int topk, float* out_dev, void* workspace_dev, void* stream);
 
+/* ZCA whitening + L2 normalisation of segment embeddings — whiten_l2(embs) (diar_diag.py:187-194; call site
+ * :352, between embedding and clustering): X = embs - mean (f32); C = cov(X) (f64); W = (C + 1e-6 I)^(-1/2)
+ * through the eigendecomposition of C (one-sided Jacobi on the device; the reference's SVD of the symmetric
+ * PSD C is the same decomposition); out = X W, rows divided by (norm + 1e-9).  x_dev [N, D] f32, out_dev [N, D]
+ * f64.  N >= 2, D % 32 == 0, D <= 192.  sweeps_host, if not NULL, receives the number of Jacobi sweeps
+ * (synchronises the stream).  workspace_dev: sd_whiten_workspace_bytes(N, D) bytes. */
+size_t sd_whiten_workspace_bytes(int N, int D);
+int sd_whiten_l2_f64(const float* x_dev, int N, int D, double* out_dev, void* workspace_dev, int32_t* sweeps_host,
+                     void* stream);
+
 /* hysteresis_binarize(probs, on, off) (vad.py:59-74; diar_diag.py:331): mask[i] = talking after frame i,
  * where a silent state turns on at p >= on and a talking state turns off at p < off (compared in f64, as
  * numba does).  probs_dev [n] f32 (probs_f64 = 0) or f64 (= 1); mask_dev [n] u8 (0 / 1).  A parallel scan

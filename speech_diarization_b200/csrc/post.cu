@@ -23,7 +23,7 @@ namespace {
 
 // ================================================================================ Viterbi
 constexpr int VT_CHUNK = 128;   // frames per back-tracking chunk
-constexpr int VT_PF = 8;        // score rows prefetched ahead of the recursion
+constexpr int VT_PF = 32;       // score rows prefetched ahead of the recursion (covers ~1 us of DRAM latency)
 
 template <typename ScoreT>
 __device__ __forceinline__ float vt_emit(float prev_best, ScoreT s);
@@ -34,74 +34,128 @@ template <> __device__ __forceinline__ float vt_emit<double>(float p, double s) 
 }
 
 // Forward recursion: ONE warp, lane j = state j (K <= 32).  The T steps are strictly dependent, so the
-// kernel is a latency chain (K shuffles, K adds, K compare-selects per step); score rows are prefetched
-// VT_PF steps ahead so no global-memory latency sits on that chain.  ptr[t][j] (u8) is written behind it.
-template <typename ScoreT>
+// kernel is a latency chain (K shuffles, K adds, K compare-selects per step).  Score rows are fetched a
+// BLOCK of VT_PF steps ahead into a second register buffer, all loads issued together at the top of a block,
+// so no load sits between the steps (single loads interleaved with the steps share scoreboard slots and
+// stalled every step: 250 cycles/step measured).  K <= 8 is unrolled at compile time (KT; KT = 0 = generic
+// loop).  Back-pointers of four consecutive steps are packed into one u32 per state: ptr4[t / 4][j].
+template <typename ScoreT, int KT>
+__device__ __forceinline__ float vt_step(float dp, ScoreT s, int K, int lane, float log_stay, float log_move, int& arg) {
+  float best = __fadd_rn(__shfl_sync(0xffffffffu, dp, 0), 0 == lane ? log_stay : log_move);
+  arg = 0;
+  if (KT > 0) {
+#pragma unroll
+    for (int i = 1; i < KT; ++i) {
+      const float v = __fadd_rn(__shfl_sync(0xffffffffu, dp, i), i == lane ? log_stay : log_move);
+      if (v > best) { best = v; arg = i; }       // strict '>' : first maximum, as np.argmax
+    }
+  } else {
+    for (int i = 1; i < K; ++i) {
+      const float v = __fadd_rn(__shfl_sync(0xffffffffu, dp, i), i == lane ? log_stay : log_move);
+      if (v > best) { best = v; arg = i; }
+    }
+  }
+  return vt_emit<ScoreT>(best, s);
+}
+
+template <typename ScoreT, int KT>
 __global__ void __launch_bounds__(32)
-viterbi_forward_kernel(const ScoreT* __restrict__ scores, int T, int K, float log_stay, float log_move,
-                       uint8_t* __restrict__ ptr, int* __restrict__ last_state) {
+viterbi_forward_kernel(const ScoreT* __restrict__ scores, int T, int K_rt, float log_stay, float log_move,
+                       uint32_t* __restrict__ ptr4, int* __restrict__ last_state) {
+  const int K = KT > 0 ? KT : K_rt;
   const int lane = threadIdx.x;
   const bool act = lane < K;
   const int col = act ? lane : 0;
-  ScoreT pf[VT_PF];
+  ScoreT cur[VT_PF], nxt[VT_PF];
+  // block b covers steps t = b * VT_PF .. b * VT_PF + VT_PF - 1 (t = 0 is the initialisation)
 #pragma unroll
-  for (int i = 0; i < VT_PF; ++i) pf[i] = (1 + i < T) ? scores[static_cast<size_t>(1 + i) * K + col] : ScoreT(0);
-  float dp = static_cast<float>(scores[col]);   // dp[0] = scores[0] (stored as f32)
-  for (int t0 = 1; t0 < T; t0 += VT_PF) {
+  for (int u = 0; u < VT_PF; ++u) cur[u] = u < T ? scores[static_cast<size_t>(u) * K + col] : ScoreT(0);
+  float dp = static_cast<float>(cur[0]);   // dp[0] = scores[0] (stored as f32)
+  for (int t0 = 0; t0 < T; t0 += VT_PF) {
 #pragma unroll
     for (int u = 0; u < VT_PF; ++u) {
-      const int t = t0 + u;
-      if (t < T) {
-        const ScoreT s = pf[u];
-        const int tn = t + VT_PF;
-        pf[u] = tn < T ? scores[static_cast<size_t>(tn) * K + col] : ScoreT(0);
-        float best = -INFINITY;
-        int arg = 0;
-        for (int i = 0; i < K; ++i) {
-          const float v = __fadd_rn(__shfl_sync(0xffffffffu, dp, i), i == lane ? log_stay : log_move);
-          if (v > best || i == 0) { best = v; arg = i; }   // strict '>' : first maximum, as np.argmax
-        }
-        dp = vt_emit<ScoreT>(best, s);
-        if (act) ptr[static_cast<size_t>(t) * K + lane] = static_cast<uint8_t>(arg);
-      }
+      const int tn = t0 + VT_PF + u;
+      nxt[u] = tn < T ? scores[static_cast<size_t>(tn) * K + col] : ScoreT(0);
     }
+#pragma unroll
+    for (int u4 = 0; u4 < VT_PF; u4 += 4) {
+      uint32_t packed = 0;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int t = t0 + u4 + v;
+        if (t >= 1 && t < T) {
+          int arg;
+          dp = vt_step<ScoreT, KT>(dp, cur[u4 + v], K, lane, log_stay, log_move, arg);
+          packed |= static_cast<uint32_t>(arg) << (8 * v);
+        }
+      }
+      if (act && t0 + u4 < T) ptr4[static_cast<size_t>((t0 + u4) >> 2) * K + lane] = packed;
+    }
+#pragma unroll
+    for (int u = 0; u < VT_PF; ++u) cur[u] = nxt[u];
   }
   // path[-1] = argmax(dp[-1]) (first maximum)
-  float best = -INFINITY;
+  float best = __shfl_sync(0xffffffffu, dp, 0);
   int arg = 0;
-  for (int i = 0; i < K; ++i) {
+  for (int i = 1; i < K; ++i) {
     const float v = __shfl_sync(0xffffffffu, dp, i);
-    if (v > best || i == 0) { best = v; arg = i; }
+    if (v > best) { best = v; arg = i; }
   }
   if (lane == 0) *last_state = arg;
+}
+
+template <typename ScoreT>
+void launch_viterbi_forward(const void* scores, int T, int K, float ls, float lm, uint32_t* ptr, int* last, cudaStream_t st) {
+  const ScoreT* sc = static_cast<const ScoreT*>(scores);
+  switch (K) {
+    case 2: viterbi_forward_kernel<ScoreT, 2><<<1, 32, 0, st>>>(sc, T, K, ls, lm, ptr, last); break;
+    case 3: viterbi_forward_kernel<ScoreT, 3><<<1, 32, 0, st>>>(sc, T, K, ls, lm, ptr, last); break;
+    case 4: viterbi_forward_kernel<ScoreT, 4><<<1, 32, 0, st>>>(sc, T, K, ls, lm, ptr, last); break;
+    case 5: viterbi_forward_kernel<ScoreT, 5><<<1, 32, 0, st>>>(sc, T, K, ls, lm, ptr, last); break;
+    case 6: viterbi_forward_kernel<ScoreT, 6><<<1, 32, 0, st>>>(sc, T, K, ls, lm, ptr, last); break;
+    case 7: viterbi_forward_kernel<ScoreT, 7><<<1, 32, 0, st>>>(sc, T, K, ls, lm, ptr, last); break;
+    case 8: viterbi_forward_kernel<ScoreT, 8><<<1, 32, 0, st>>>(sc, T, K, ls, lm, ptr, last); break;
+    default: viterbi_forward_kernel<ScoreT, 0><<<1, 32, 0, st>>>(sc, T, K, ls, lm, ptr, last); break;
+  }
+}
+
+__device__ __forceinline__ int vt_ptr(const uint32_t* __restrict__ ptr4, int t, int K, int st) {
+  return (ptr4[static_cast<size_t>(t >> 2) * K + st] >> (8 * (t & 3))) & 0xff;
 }
 
 // Back-tracking is a composition of the maps  s_{t} = ptr[t+1][s_{t+1}],  which is associative:
 // (1) every chunk composes its maps for all K possible end states, (2) one warp chains the chunk maps,
 // (3) every chunk re-walks with its now-known end state and writes the path.
 __global__ void __launch_bounds__(32)
-viterbi_chunk_maps_kernel(const uint8_t* __restrict__ ptr, int T, int K, int32_t* __restrict__ maps) {
+viterbi_chunk_maps_kernel(const uint32_t* __restrict__ ptr4, int T, int K, int32_t* __restrict__ maps) {
   const int c = blockIdx.x, s = threadIdx.x;
   if (s >= K) return;
   const int lo = c * VT_CHUNK, hi = min(lo + VT_CHUNK, T - 1);   // states at times lo .. hi
   int st = s;
-  for (int t = hi; t > lo; --t) st = ptr[static_cast<size_t>(t) * K + st];
+  for (int t = hi; t > lo; --t) st = vt_ptr(ptr4, t, K, st);
   maps[c * K + s] = st;   // state at time lo given state s at time hi
 }
 
-__global__ void __launch_bounds__(32)
+constexpr int VT_CHAIN_SMEM = 8192;   // chunk-map entries staged in shared memory (T*K <= 1 M)
+__global__ void __launch_bounds__(256)
 viterbi_chain_kernel(const int32_t* __restrict__ maps, int n_chunks, int K, const int* __restrict__ last_state,
                      int32_t* __restrict__ end_state) {
+  __shared__ int32_t sm[VT_CHAIN_SMEM];
+  const bool staged = n_chunks * K <= VT_CHAIN_SMEM;
+  if (staged) {
+    for (int i = threadIdx.x; i < n_chunks * K; i += 256) sm[i] = maps[i];
+    __syncthreads();
+  }
   if (threadIdx.x != 0) return;
   int st = *last_state;
   for (int c = n_chunks - 1; c >= 0; --c) {
     end_state[c] = st;
-    st = maps[c * K + st];
+    st = staged ? sm[c * K + st] : maps[c * K + st];
   }
 }
 
 __global__ void __launch_bounds__(32)
-viterbi_walk_kernel(const uint8_t* __restrict__ ptr, int T, int K, const int32_t* __restrict__ end_state,
+viterbi_walk_kernel(const uint32_t* __restrict__ ptr4, int T, int K, const int32_t* __restrict__ end_state,
                     int32_t* __restrict__ path) {
   if (threadIdx.x != 0) return;
   const int c = blockIdx.x;
@@ -109,7 +163,7 @@ viterbi_walk_kernel(const uint8_t* __restrict__ ptr, int T, int K, const int32_t
   int st = end_state[c];
   if (hi == T - 1) path[hi] = st;
   for (int t = hi; t > lo; --t) {
-    st = ptr[static_cast<size_t>(t) * K + st];
+    st = vt_ptr(ptr4, t, K, st);
     path[t - 1] = st;
   }
 }
@@ -441,7 +495,7 @@ mask_segments_kernel(const uint8_t* __restrict__ mask, int n, int min_speech, in
 extern "C" size_t sd_viterbi_workspace_bytes(int T, int K) {
   if (T < 1 || K < 1) return 0;
   const size_t n_chunks = (static_cast<size_t>(T) + VT_CHUNK - 1) / VT_CHUNK;
-  return align256(static_cast<size_t>(T) * K) + align256(n_chunks * K * 4) + align256(n_chunks * 4) + 256;
+  return align256((static_cast<size_t>(T) / 4 + 1) * K * 4) + align256(n_chunks * K * 4) + align256(n_chunks * 4) + 256;
 }
 
 extern "C" int sd_viterbi_hmm(const void* scores_dev, int scores_f64, int T, int K, float log_stay, float log_move,
@@ -451,16 +505,14 @@ extern "C" int sd_viterbi_hmm(const void* scores_dev, int scores_f64, int T, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_chunks = (T + VT_CHUNK - 1) / VT_CHUNK;
   uint8_t* base = static_cast<uint8_t*>(workspace_dev);
-  uint8_t* ptr = base;
-  int32_t* maps = reinterpret_cast<int32_t*>(base + align256(static_cast<size_t>(T) * K));
+  uint32_t* ptr = reinterpret_cast<uint32_t*>(base);
+  int32_t* maps = reinterpret_cast<int32_t*>(base + align256((static_cast<size_t>(T) / 4 + 1) * K * 4));
   int32_t* end_state = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(maps) + align256(static_cast<size_t>(n_chunks) * K * 4));
   int* last_state = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(end_state) + align256(static_cast<size_t>(n_chunks) * 4));
-  if (scores_f64)
-    viterbi_forward_kernel<double><<<1, 32, 0, st>>>(static_cast<const double*>(scores_dev), T, K, log_stay, log_move, ptr, last_state);
-  else
-    viterbi_forward_kernel<float><<<1, 32, 0, st>>>(static_cast<const float*>(scores_dev), T, K, log_stay, log_move, ptr, last_state);
+  if (scores_f64) launch_viterbi_forward<double>(scores_dev, T, K, log_stay, log_move, ptr, last_state, st);
+  else launch_viterbi_forward<float>(scores_dev, T, K, log_stay, log_move, ptr, last_state, st);
   viterbi_chunk_maps_kernel<<<n_chunks, 32, 0, st>>>(ptr, T, K, maps);
-  viterbi_chain_kernel<<<1, 32, 0, st>>>(maps, n_chunks, K, last_state, end_state);
+  viterbi_chain_kernel<<<1, 256, 0, st>>>(maps, n_chunks, K, last_state, end_state);
   viterbi_walk_kernel<<<n_chunks, 32, 0, st>>>(ptr, T, K, end_state, path_dev);
   SD_CUDA_OK(cudaGetLastError());
   count_launch(4);

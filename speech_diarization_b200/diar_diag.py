@@ -1,7 +1,7 @@
 """Drop-in for the hot-path pieces of /root/reference/diar_diag.py:
 ``cluster_embeddings`` (:213-229, "agglo" branch), the ``frame_audio`` duplicate (:48-56), and the score
-post-processing of its pipeline: ``asnorm_scores`` (:196-208) and ``viterbi_hmm`` (:231-247)
-(SURVEY.md §8f rank 4).  Whitening and plotting are not built."""
+post-processing of its pipeline: ``whiten_l2`` (:187-194), ``asnorm_scores`` (:196-208) and ``viterbi_hmm``
+(:231-247).  Audio loading, plotting and the JSON / SRT / CSV writers are not built."""
 from __future__ import annotations
 
 import numpy as np
@@ -35,6 +35,13 @@ def cluster_embeddings(embs: np.ndarray, method="hdbscan", cos_thr: float = 0.68
     if method == "hdbscan":
         raise NotImplementedError("method='hdbscan' is outside the B200 hot path (SURVEY.md §2 #9-10); use 'agglo'")
     raise ValueError("method 必须是 hdbscan 或 agglo")      # diar_diag.py:228
+
+
+def whiten_l2(embs: np.ndarray) -> np.ndarray:
+    """diar_diag.py:187-194 — centre, ZCA-whiten with (cov + 1e-6 I)^(-1/2), L2-normalise; float64 [N, D].
+    Covariance, eigendecomposition (Jacobi) and the projection all run on the GPU in f64."""
+    x = to_cuda_embeddings(embs)
+    return postproc.whiten_l2_device(x).cpu().numpy()
 
 
 def asnorm_scores(query_embs: np.ndarray, ref_centers: np.ndarray, cohort_embs: np.ndarray,

@@ -44,6 +44,21 @@ def asnorm_device(q: torch.Tensor, r: torch.Tensor, c: torch.Tensor, topk: int =
     return out
 
 
+def whiten_l2_device(x: torch.Tensor, return_sweeps: bool = False):
+    """whiten_l2 (diar_diag.py:187-194) on a CUDA f32 [N, D] tensor -> CUDA f64 [N, D] (unit rows)."""
+    import ctypes
+    lib = _lib.load()
+    N, D = x.shape
+    out = torch.empty((N, D), dtype=torch.float64, device=x.device)
+    ws = torch.empty((lib.sd_whiten_workspace_bytes(N, D),), dtype=torch.uint8, device=x.device)
+    sweeps = ctypes.c_int32(0)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sd_whiten_l2_f64(x.data_ptr(), N, D, out.data_ptr(), ws.data_ptr(),
+                                        ctypes.byref(sweeps) if return_sweeps else None, _lib.stream_ptr()),
+                   "sd_whiten_l2_f64")
+    return (out, sweeps.value) if return_sweeps else out
+
+
 def hysteresis_device(probs: torch.Tensor, on: float = 0.6, off: float = 0.4) -> torch.Tensor:
     """hysteresis_binarize (vad.py:59-74) on a CUDA [n] f32 / f64 tensor -> uint8 mask [n]."""
     lib = _lib.load()

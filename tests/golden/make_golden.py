@@ -115,6 +115,12 @@ def make_post_golden():
     Xc, _ = synth_embeddings(50, 3, 0.1, 12)
     out["as_cohort"] = Xc
     out["as_small"] = ref_dd.asnorm_scores(X[:70], out["as_cent"], Xc, topk=200)       # topk > cohort size
+    # ---- whitening (diar_diag.py:187-194): well-conditioned (N > D) and rank-deficient (N < D) covariance
+    Xw, _ = synth_embeddings(240, 4, 0.3, 14)
+    out["wh_X"] = (Xw * 7.5).astype(np.float32)                      # raw ECAPA embeddings are not unit-norm
+    out["wh_out"] = ref_dd.whiten_l2(out["wh_X"])
+    out["wh_X_small"] = out["wh_X"][:60]
+    out["wh_out_small"] = ref_dd.whiten_l2(out["wh_X_small"])
     # ---- Viterbi: f32 scores (from AS-norm), f64 scores, tie-heavy integer scores, T = 1, K = 2
     out["vt_scores_as"] = out["as_self"].astype(np.float32)
     out["vt_path_as"] = ref_dd.viterbi_hmm(out["vt_scores_as"], alpha=0.995)

@@ -127,3 +127,36 @@ def test_vad_mask_ops_match_oracle_at_chunk_boundaries(n, seed):
                                       po.morph_open_close(m0, 10.0, open_ms, close_ms))
     for args in ((250.0, 100.0, 80.0), (10.0, 0.0, 0.0), (400.0, 300.0, 200.0)):
         assert vad.mask_to_segments(m0, 10.0, *args) == po.mask_to_segments(m0, 10.0, *args)
+
+
+# ---------------------------------------------------------------------------------- whitening
+def test_whiten_matches_reference_golden():
+    """f64 on both sides; the only f32 step (the column mean) is summed in a different order, which moves the
+    unit-norm output by < 1e-6.  The rank-deficient case (N = 60 < D) amplifies noise directions by
+    1/sqrt(1e-6) = 1000 — the f32 centring residue of X in the null space of C, ~1e-7 relative, becomes 1e-4 of the
+    row — and is held to 1e-4 (measured 2.3e-5)."""
+    from speech_diarization_b200 import diar_diag
+    g = golden("post_ref.npz")
+    got = diar_diag.whiten_l2(g["wh_X"])
+    assert got.dtype == np.float64 and got.shape == g["wh_out"].shape
+    assert np.abs(got - g["wh_out"]).max() <= 1e-6, np.abs(got - g["wh_out"]).max()
+    got = diar_diag.whiten_l2(g["wh_X_small"])
+    assert np.abs(got - g["wh_out_small"]).max() <= 1e-4, np.abs(got - g["wh_out_small"]).max()
+
+
+@pytest.mark.parametrize("N,scale", [(5000, 12.0), (20000, 1.0), (193, 30.0)])
+def test_whiten_matches_oracle(N, scale):
+    from speech_diarization_b200 import postproc
+    X, _ = synth_emb(N, 6, 0.4, N)
+    X = (X * scale).astype(np.float32)
+    out, sweeps = postproc.whiten_l2_device(torch.from_numpy(X).cuda(), return_sweeps=True)
+    got = out.cpu().numpy()
+    ref = _po().whiten_l2(X)
+    assert 2 <= sweeps < 40, sweeps                       # the Jacobi iteration converged
+    assert np.abs(got - ref).max() <= 2e-6, np.abs(got - ref).max()
+    np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-8)
+    # whitened data has identity covariance (up to the 1e-6 ridge) before the row normalisation: check through
+    # the property that survives it — off-diagonal correlations vanish
+    if N >= 5000:
+        c = np.corrcoef(got.T)
+        assert np.abs(c - np.eye(192)).max() < 0.2

@@ -213,3 +213,12 @@ def test_post_oracle_matches_reference_vad_mask_ops(tag):
         assert len(segs) > 5 and m0.any() and not m0.all()
         assert po.mask_to_segments(np.zeros(100, bool), 10.0) == []
         np.testing.assert_array_equal(np.array(po.mask_to_segments(np.ones(100, bool), 10.0)), g["vad_full_segs"])
+
+
+def test_post_oracle_matches_reference_whiten():
+    from oracle import post_oracle as po
+    g = golden("post_ref.npz")
+    np.testing.assert_array_equal(po.whiten_l2(g["wh_X"]), g["wh_out"])
+    np.testing.assert_array_equal(po.whiten_l2(g["wh_X_small"]), g["wh_out_small"])
+    assert g["wh_out"].dtype == np.float64
+    np.testing.assert_allclose(np.linalg.norm(g["wh_out"], axis=1), 1.0, atol=1e-8)
