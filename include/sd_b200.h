@@ -217,6 +217,16 @@ size_t sd_whiten_workspace_bytes(int N, int D);
 int sd_whiten_l2_f64(const float* x_dev, int N, int D, double* out_dev, void* workspace_dev, int32_t* sweeps_host,
                      void* stream);
 
+/* Unit-norm cluster centres — `m = embs[labels == k].mean(0); m /= norm(m) + 1e-9` for k = 0 .. K-1
+ * (diar_diag.py:377-383).  x_dev [N, D] f64 (the whitened embeddings), labels_dev [N] int32 in [0, K);
+ * out_f64_dev / out_f32_dev [K, D] (either may be NULL).  D <= 256. */
+int sd_cluster_centers_f64(const double* x_dev, const int32_t* labels_dev, int N, int D, int K,
+                           double* out_f64_dev, float* out_f32_dev, void* stream);
+
+/* scores[i, k] = <x_i, c_k> — `scores = embs @ centers.T` (diar_diag.py:386).  x_dev [N, D], cent_dev [K, D],
+ * out_dev [N, K], all f32. */
+int sd_dot_scores(const float* x_dev, const float* cent_dev, int N, int K, int D, float* out_dev, void* stream);
+
 /* hysteresis_binarize(probs, on, off) (vad.py:59-74; diar_diag.py:331): mask[i] = talking after frame i,
  * where a silent state turns on at p >= on and a talking state turns off at p < off (compared in f64, as
  * numba does).  probs_dev [n] f32 (probs_f64 = 0) or f64 (= 1); mask_dev [n] u8 (0 / 1).  A parallel scan

@@ -51,6 +51,8 @@ SIGNATURES = {
     "sd_asnorm_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sd_whiten_workspace_bytes": (c_size_t, [c_int, c_int]),
     "sd_whiten_l2_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(c_int32), c_void_p]),
+    "sd_cluster_centers_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "sd_dot_scores": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sd_hysteresis_u8": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
     "sd_morph_open_close_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sd_mask_segments_workspace_bytes": (c_size_t, [c_int]),

@@ -303,6 +303,22 @@ asnorm_combine_kernel(const float* __restrict__ qn, const float* __restrict__ rn
   }
 }
 
+// scores[i][k] = <x_i, c_k>  (diar_diag.py:386, `embs @ centers.T`); one warp per row.
+__global__ void __launch_bounds__(256)
+dot_scores_kernel(const float* __restrict__ x, const float* __restrict__ cent, int N, int K, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < N; row += gridDim.x * 8) {
+    const float* p = x + static_cast<size_t>(row) * D;
+    for (int k = 0; k < K; ++k) {
+      const float* c = cent + static_cast<size_t>(k) * D;
+      float s = 0.f;
+      for (int i = lane; i < D; i += 32) s = fmaf(p[i], c[i], s);
+      s = warp_sum(s);
+      if (lane == 0) out[static_cast<size_t>(row) * K + k] = s;
+    }
+  }
+}
+
 int cohort_distances(const __half* a_split, int rows_total, int row0, int rows, const __half* c_split, int nc, int D,
                      float* out, cudaStream_t st) {
   GemmParams P;
@@ -333,6 +349,41 @@ int cohort_distances(const __half* a_split, int rows_total, int row0, int rows, 
 
 constexpr int AS_ROW_BLOCK = 4096;   // query rows per distance block (bounds the workspace)
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// Unit-norm cluster centres (diar_diag.py:377-383): centre k = mean of the rows labelled k, divided by
+// (norm + 1e-9).  One CTA per cluster, thread = column, f64 accumulation in row order (as numpy's mean(0)).
+__global__ void __launch_bounds__(256)
+cluster_centers_kernel(const double* __restrict__ x, const int32_t* __restrict__ labels, int N, int D,
+                       double* __restrict__ out64, float* __restrict__ out32) {
+  __shared__ double red[8];
+  __shared__ int lab[1024];
+  const int k = blockIdx.x, d = threadIdx.x;
+  double acc = 0.0;
+  int cnt = 0;
+  for (int base = 0; base < N; base += 1024) {
+    __syncthreads();
+    for (int i = d; i < 1024; i += 256) lab[i] = base + i < N ? labels[base + i] : -1;
+    __syncthreads();
+    const int n = min(1024, N - base);
+    for (int i = 0; i < n; ++i)
+      if (lab[i] == k) {
+        ++cnt;
+        if (d < D) acc += x[static_cast<size_t>(base + i) * D + d];
+      }
+  }
+  const double m = cnt > 0 ? acc / static_cast<double>(cnt) : 0.0;
+  double q = d < D ? m * m : 0.0;
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((d & 31) == 0) red[d >> 5] = q;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < 8; ++w) t += red[w];
+  if (d < D) {
+    const double v = m / (sqrt(t) + 1e-9);
+    if (out64) out64[static_cast<size_t>(k) * D + d] = v;
+    if (out32) out32[static_cast<size_t>(k) * D + d] = static_cast<float>(v);
+  }
+}
 
 // ================================================================================ VAD mask ops
 // Block-wide inclusive scan over 1024 threads (int).
@@ -639,6 +690,27 @@ extern "C" int sd_mask_segments_i32(const uint8_t* mask_dev, int n, int min_spee
   int32_t* run_s = static_cast<int32_t*>(workspace_dev);
   int32_t* run_e = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(workspace_dev) + align256((static_cast<size_t>(n) / 2 + 2) * 4));
   mask_segments_kernel<<<1, 1024, 0, st>>>(mask_dev, n, min_speech_frames, min_gap_frames, run_s, run_e, seg_dev, count_dev);
+  SD_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return SD_OK;
+}
+
+extern "C" int sd_cluster_centers_f64(const double* x_dev, const int32_t* labels_dev, int N, int D, int K,
+                                      double* out_f64_dev, float* out_f32_dev, void* stream) {
+  if (!x_dev || !labels_dev || (!out_f64_dev && !out_f32_dev) || N < 1 || D < 1 || D > 256 || K < 1)
+    return fail(SD_ERR_ARG, "sd_cluster_centers_f64: bad arguments N=%d D=%d K=%d", N, D, K);
+  cluster_centers_kernel<<<K, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, labels_dev, N, D, out_f64_dev, out_f32_dev);
+  SD_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return SD_OK;
+}
+
+extern "C" int sd_dot_scores(const float* x_dev, const float* cent_dev, int N, int K, int D, float* out_dev, void* stream) {
+  if (!x_dev || !cent_dev || !out_dev || N < 0 || K < 1 || D < 1) return fail(SD_ERR_ARG, "sd_dot_scores: bad arguments");
+  if (N == 0) return SD_OK;
+  int grid = (N + 7) / 8;
+  if (grid > 148 * 8) grid = 148 * 8;
+  dot_scores_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, cent_dev, N, K, D, out_dev);
   SD_CUDA_OK(cudaGetLastError());
   count_launch();
   return SD_OK;

@@ -59,6 +59,29 @@ def whiten_l2_device(x: torch.Tensor, return_sweeps: bool = False):
     return (out, sweeps.value) if return_sweeps else out
 
 
+def cluster_centers_device(x64: torch.Tensor, labels: torch.Tensor, K: int) -> torch.Tensor:
+    """Unit-norm centres of K clusters (diar_diag.py:377-383): CUDA f64 [N, D] + int32 labels -> CUDA f32 [K, D]."""
+    lib = _lib.load()
+    N, D = x64.shape
+    out = torch.empty((K, D), dtype=torch.float32, device=x64.device)
+    with torch.cuda.device(x64.device):
+        _lib.check(lib.sd_cluster_centers_f64(x64.data_ptr(), labels.data_ptr(), N, D, K, None, out.data_ptr(),
+                                              _lib.stream_ptr()), "sd_cluster_centers_f64")
+    return out
+
+
+def dot_scores_device(x: torch.Tensor, cent: torch.Tensor) -> torch.Tensor:
+    """embs @ centers.T (diar_diag.py:386) on CUDA f32 tensors -> [N, K] f32."""
+    lib = _lib.load()
+    N, D = x.shape
+    K = cent.shape[0]
+    out = torch.empty((N, K), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sd_dot_scores(x.data_ptr(), cent.data_ptr(), N, K, D, out.data_ptr(), _lib.stream_ptr()),
+                   "sd_dot_scores")
+    return out
+
+
 def hysteresis_device(probs: torch.Tensor, on: float = 0.6, off: float = 0.4) -> torch.Tensor:
     """hysteresis_binarize (vad.py:59-74) on a CUDA [n] f32 / f64 tensor -> uint8 mask [n]."""
     lib = _lib.load()

@@ -121,6 +121,32 @@ def make_post_golden():
     out["wh_out"] = ref_dd.whiten_l2(out["wh_X"])
     out["wh_X_small"] = out["wh_X"][:60]
     out["wh_out_small"] = ref_dd.whiten_l2(out["wh_X_small"])
+    # ---- main()'s post-embedding path (diar_diag.py:352-411), the reference's own functions in its order.
+    # Within-speaker variation is confined to 2 nuisance directions: isotropic noise would leave no cluster
+    # structure after ZCA whitening (every direction gets unit variance) and make the labels chaotic.
+    rng = np.random.default_rng(15)
+    Np = 300
+    cp = rng.standard_normal((3, 192)); cp /= np.linalg.norm(cp, axis=1, keepdims=True)
+    up = rng.standard_normal((2, 192)); up /= np.linalg.norm(up, axis=1, keepdims=True)
+    labp = np.repeat(rng.integers(0, 3, Np // 10 + 1), 10)[:Np]                        # speaker turns of 10 segments
+    Xp = ((cp[labp] + (0.15 * rng.standard_normal((Np, 2))) @ up) * 9.0).astype(np.float32)
+    segs_p = np.stack([np.arange(Np) * 1.5, np.arange(Np) * 1.5 + 1.45], axis=1)
+    segs_p[::7, 0] += 0.3                                                            # some gaps > 0.1 s
+    for tag, (wh, asn, vbx, thr) in {"full": (1, 1, 1, 0.1), "plain": (0, 0, 0, 0.68), "wh_argmax": (1, 1, 0, 0.1),
+                                     "vbx_raw": (0, 0, 1, 0.68)}.items():
+        e = ref_dd.whiten_l2(Xp) if wh else Xp
+        lab = ref_dd.cluster_embeddings(e, method="agglo", cos_thr=thr)
+        uniq = sorted([u for u in np.unique(lab) if u != -1])
+        cents = []
+        for k in uniq:
+            m = e[lab == k].mean(0); m /= (np.linalg.norm(m) + 1e-9); cents.append(m)
+        cents = np.vstack(cents)
+        sc = e @ cents.T
+        if asn:
+            sc = ref_dd.asnorm_scores(e, cents, e, topk=min(200, len(e)))
+        fin = ref_dd.viterbi_hmm(sc, alpha=0.995) if vbx else np.argmax(sc, axis=1)
+        out[f"pipe_{tag}_labels"], out[f"pipe_{tag}_final"] = lab, np.asarray(fin)
+    out["pipe_X"], out["pipe_segs"], out["pipe_true"] = Xp, segs_p, labp
     # ---- Viterbi: f32 scores (from AS-norm), f64 scores, tie-heavy integer scores, T = 1, K = 2
     out["vt_scores_as"] = out["as_self"].astype(np.float32)
     out["vt_path_as"] = ref_dd.viterbi_hmm(out["vt_scores_as"], alpha=0.995)

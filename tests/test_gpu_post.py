@@ -160,3 +160,66 @@ def test_whiten_matches_oracle(N, scale):
     if N >= 5000:
         c = np.corrcoef(got.T)
         assert np.abs(c - np.eye(192)).max() < 0.2
+
+
+# ---------------------------------------------------------------------------------- diar_diag pipeline
+@pytest.mark.parametrize("tag,wh,asn,vbx,thr", [("full", 1, 1, 1, 0.1), ("plain", 0, 0, 0, 0.68),
+                                                 ("wh_argmax", 1, 1, 0, 0.1), ("vbx_raw", 0, 0, 1, 0.68)])
+def test_label_segments_matches_reference_pipeline(tag, wh, asn, vbx, thr):
+    """main()'s post-embedding path (diar_diag.py:352-411) in one GPU-resident call: cluster labels and final
+    speaker path equal the reference's up to the numbering of the clusters; merged segments have the same
+    boundaries."""
+    from oracle import cluster_oracle as co
+    from speech_diarization_b200 import diar_diag
+    po = _po()
+    g = golden("post_ref.npz")
+    segs = [tuple(x) for x in g["pipe_segs"]]
+    merged, final, labels = diar_diag.label_segments(g["pipe_X"], segs, whiten=wh, asnorm=asn, cluster="agglo",
+                                                     cos_thr=thr, use_vbx=vbx)
+    assert co.same_partition(labels, g[f"pipe_{tag}_labels"])
+    assert co.same_partition(final, g[f"pipe_{tag}_final"])
+    ref_merged = po.merge_segments(segs, g[f"pipe_{tag}_final"], gap=0.1)
+    assert [(a, b) for a, b, _ in merged] == [(a, b) for a, b, _ in ref_merged]
+    assert co.same_partition(np.array([m[2] for m in merged]), np.array([m[2] for m in ref_merged]))
+
+
+def test_label_segments_rejects_hdbscan():
+    from speech_diarization_b200 import diar_diag
+    with pytest.raises(NotImplementedError):
+        diar_diag.label_segments(np.zeros((4, 192), np.float32), [(0, 1)] * 4, cluster="hdbscan")
+
+
+def test_cluster_centers_and_dot_scores_match_numpy():
+    from speech_diarization_b200 import postproc
+    X, lab = synth_emb(3000, 5, 0.1, 9)
+    x64 = torch.from_numpy(X.astype(np.float64)).cuda()
+    cent = postproc.cluster_centers_device(x64, torch.from_numpy(lab.astype(np.int32)).cuda(), 5)
+    ref = np.stack([X.astype(np.float64)[lab == k].mean(0) for k in range(5)])
+    ref /= np.linalg.norm(ref, axis=1, keepdims=True) + 1e-9
+    assert np.abs(cent.cpu().numpy() - ref.astype(np.float32)).max() <= 1e-7
+    sc = postproc.dot_scores_device(torch.from_numpy(X).cuda(), cent)
+    assert np.abs(sc.cpu().numpy() - X @ ref.astype(np.float32).T).max() <= 1e-5
+
+
+def test_speaker_encoder_embed_matches_oracle(oracle_model):
+    """SpeakerEncoder(...).embed(y, sr) (diar_diag.py:161-170): one utterance -> float32 [192]."""
+    from oracle import ecapa_oracle
+    from speech_diarization_b200 import diar_diag, speech_encode
+    from conftest import synth_wave
+    speech_encode.register_ecapa_state_dict(oracle_model.state_dict())
+    try:
+        enc = diar_diag.SpeakerEncoder("speechbrain-ecapa", device="cuda")
+        y = synth_wave(1, 11000, 3)[0]
+        e = enc.embed(y, 16000)
+        assert e.dtype == np.float32 and e.shape == (192,)
+        with torch.inference_mode():
+            ref = ecapa_oracle.encode_batch(oracle_model, torch.from_numpy(y)[None]).squeeze().numpy()
+        cos = float(np.dot(e, ref) / (np.linalg.norm(e) * np.linalg.norm(ref)))
+        assert 1 - cos < 1e-4, 1 - cos
+        with pytest.raises(NotImplementedError):
+            enc.embed(y, 8000)
+        with pytest.raises(ValueError):
+            diar_diag.SpeakerEncoder("kaldi")
+        np.testing.assert_array_equal(diar_diag.pad_with_context(np.arange(100), 10, 2.0, 5.0, 0.5), np.arange(15, 55))
+    finally:
+        speech_encode.register_ecapa_state_dict(None)

@@ -222,3 +222,17 @@ def test_post_oracle_matches_reference_whiten():
     np.testing.assert_array_equal(po.whiten_l2(g["wh_X_small"]), g["wh_out_small"])
     assert g["wh_out"].dtype == np.float64
     np.testing.assert_allclose(np.linalg.norm(g["wh_out"], axis=1), 1.0, atol=1e-8)
+
+
+@pytest.mark.parametrize("tag,wh,asn,vbx,thr", [("full", 1, 1, 1, 0.1), ("plain", 0, 0, 0, 0.68),
+                                                 ("wh_argmax", 1, 1, 0, 0.1), ("vbx_raw", 0, 0, 1, 0.68)])
+def test_post_oracle_pipeline_matches_reference_functions(tag, wh, asn, vbx, thr):
+    """oracle.label_segments (diar_diag.py:352-411) against the reference's own functions chained in main()'s order."""
+    from oracle import post_oracle as po
+    g = golden("post_ref.npz")
+    segs = [tuple(x) for x in g["pipe_segs"]]
+    merged, final, labels = po.label_segments(g["pipe_X"], segs, whiten=wh, asnorm=asn, cos_thr=thr, use_vbx=vbx)
+    np.testing.assert_array_equal(labels, g[f"pipe_{tag}_labels"])
+    np.testing.assert_array_equal(final, g[f"pipe_{tag}_final"])
+    assert co.same_partition(labels, g["pipe_true"])
+    assert merged[0][0] == segs[0][0] and merged[-1][1] == segs[-1][1] and len(merged) >= 20
