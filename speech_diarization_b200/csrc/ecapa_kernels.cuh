@@ -154,27 +154,47 @@ se_hidden_kernel(const float* __restrict__ mean, const float* __restrict__ W1,
     *reinterpret_cast<float4*>(sm + i) = v;
   }
   __syncthreads();
-#pragma unroll 1
-  for (int jj = 0; jj < 4; ++jj) {
-    const int j = blockIdx.y * 32 + warp * 4 + jj;
-    if (j >= S) break;
-    const float4* w = reinterpret_cast<const float4*>(W1 + static_cast<size_t>(j) * C);
-    float acc[SE_U];
+  // The warp's 4 hidden units together, 4 column steps at a time: 16 independent 128-bit weight loads in
+  // flight per lane (one unit / two steps at a time left the kernel waiting on L2 round trips: 19 us).
+  const int j0 = blockIdx.y * 32 + warp * 4;
+  float acc[4][SE_U];
 #pragma unroll
-    for (int u = 0; u < SE_U; ++u) acc[u] = 0.f;
-#pragma unroll 2
-    for (int i = lane; i < C / 4; i += 32) {
-      const float4 wv = __ldg(w + i);
+  for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-      for (int u = 0; u < SE_U; ++u) {
-        const float4 mv = *reinterpret_cast<const float4*>(sm + u * C + 4 * i);
-        acc[u] += wv.x * mv.x + wv.y * mv.y + wv.z * mv.z + wv.w * mv.w;
+    for (int u = 0; u < SE_U; ++u) acc[jj][u] = 0.f;
+  const int n4 = C / 4;
+  for (int i0 = lane; i0 < n4; i0 += 128) {
+    float4 wv[4][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int i = i0 + 32 * s;
+        wv[s][jj] = (i < n4 && j0 + jj < S) ? __ldg(reinterpret_cast<const float4*>(W1 + static_cast<size_t>(j0 + jj) * C) + i)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int i = i0 + 32 * s;
+      if (i < n4) {
+#pragma unroll
+        for (int u = 0; u < SE_U; ++u) {
+          const float4 mv = *reinterpret_cast<const float4*>(sm + u * C + 4 * i);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            acc[jj][u] += wv[s][jj].x * mv.x + wv[s][jj].y * mv.y + wv[s][jj].z * mv.z + wv[s][jj].w * mv.w;
+        }
       }
     }
+  }
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = j0 + jj;
+    if (j >= S) break;
     const float bj = b1[j];
 #pragma unroll
     for (int u = 0; u < SE_U; ++u) {
-      const float a = warp_sum(acc[u]);
+      const float a = warp_sum(acc[jj][u]);
       if (lane == 0 && u < nb) hid[static_cast<size_t>(b0 + u) * S + j] = fmaxf(a + bj, 0.f);
     }
   }
@@ -200,19 +220,23 @@ se_scale_kernel(const float* __restrict__ hid, const float* __restrict__ W2t,
   const float bc = b2[c];
 #pragma unroll
   for (int u = 0; u < SE_U; ++u) acc[u] = bc;
-#pragma unroll 2
-  for (int j = 0; j < S; j += 4) {
-    const float w0 = __ldg(W2t + static_cast<size_t>(j) * C + c);
-    const float w1 = __ldg(W2t + static_cast<size_t>(j + 1) * C + c);
-    const float w2 = __ldg(W2t + static_cast<size_t>(j + 2) * C + c);
-    const float w3 = __ldg(W2t + static_cast<size_t>(j + 3) * C + c);
+  // 16 weight rows per step: 16 independent loads in flight per thread (S % 16 == 0 for S = 128)
+  for (int j = 0; j < S; j += 16) {
+    float w[16];
 #pragma unroll
-    for (int u = 0; u < SE_U; ++u) {
-      const float4 hv = *reinterpret_cast<const float4*>(h + u * S + j);
-      acc[u] = fmaf(hv.x, w0, acc[u]);
-      acc[u] = fmaf(hv.y, w1, acc[u]);
-      acc[u] = fmaf(hv.z, w2, acc[u]);
-      acc[u] = fmaf(hv.w, w3, acc[u]);
+    for (int q = 0; q < 16; ++q) w[q] = j + q < S ? __ldg(W2t + static_cast<size_t>(j + q) * C + c) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) {
+      if (j + q < S) {
+#pragma unroll
+        for (int u = 0; u < SE_U; ++u) {
+          const float4 hv = *reinterpret_cast<const float4*>(h + u * S + j + q);
+          acc[u] = fmaf(hv.x, w[q], acc[u]);
+          acc[u] = fmaf(hv.y, w[q + 1], acc[u]);
+          acc[u] = fmaf(hv.z, w[q + 2], acc[u]);
+          acc[u] = fmaf(hv.w, w[q + 3], acc[u]);
+        }
+      }
     }
   }
 #pragma unroll
