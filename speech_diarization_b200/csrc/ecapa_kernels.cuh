@@ -19,6 +19,8 @@ namespace sd {
 __global__ void __launch_bounds__(128)
 time_mean_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H, int C,
                  float* __restrict__ mean_out /*[B, C]*/) {
+  pdl_trigger();
+  pdl_wait();
   // utterances last to first: the producer GEMM wrote them first to last, so the most recently written
   // (still L2-resident) rows are read first instead of being evicted by this kernel's own misses
   const int b = gridDim.y - 1 - blockIdx.y;
@@ -56,6 +58,8 @@ time_mean_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H, int
 __global__ void __launch_bounds__(128)
 time_mean_std_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H, int C,
                      float* __restrict__ stats /*[B, 2C]*/, __half* __restrict__ stats_h /*[B, 2C] or null*/) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
   if (c >= C) return;
@@ -111,6 +115,8 @@ colstats_finish_kernel(const float* __restrict__ colsum, const float* __restrict
                        const float* __restrict__ shift, int C, int Tp, int T, int num_m_blocks,
                        float* __restrict__ mean_out, int ld_out, float* __restrict__ std_out,
                        __half* __restrict__ out_h) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
   const int m_lo = (b * Tp) / 128;
@@ -144,6 +150,8 @@ constexpr int SE_U = 4;
 __global__ void __launch_bounds__(256)
 se_hidden_kernel(const float* __restrict__ mean, const float* __restrict__ W1,
                  const float* __restrict__ b1, int B, int C, int S, float* __restrict__ hid) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];  // [SE_U][C]
   const int b0 = blockIdx.x * SE_U, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = min(SE_U, B - b0);
@@ -206,6 +214,8 @@ se_hidden_kernel(const float* __restrict__ mean, const float* __restrict__ W1,
 __global__ void __launch_bounds__(256)
 se_scale_kernel(const float* __restrict__ hid, const float* __restrict__ W2t,
                 const float* __restrict__ b2, int B, int C, int S, float* __restrict__ scale) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float h[SE_U * 128];
   const int b0 = blockIdx.x * SE_U, tid = threadIdx.x;
   const int nb = min(SE_U, B - b0);
@@ -250,6 +260,8 @@ __global__ void __launch_bounds__(256)
 se_apply_kernel(const __half* __restrict__ w, int ld_w, const float* __restrict__ scale,
                 const __half* __restrict__ res, int ld_res, __half* __restrict__ out, int ld_out,
                 long rows, int Tp, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int vec_per_row = C / 8;
   const long total = rows * vec_per_row;
   for (long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x; i < total;
@@ -294,6 +306,8 @@ l2norm_rows_kernel(const float* __restrict__ x, int N, int D, float eps, float* 
 __global__ void __launch_bounds__(256)
 sum_splits_kernel(const float* __restrict__ partial, int n_splits, long stride, long count,
                   float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= count) return;
   float acc = 0.f;
@@ -306,6 +320,8 @@ sum_splits_kernel(const float* __restrict__ partial, int n_splits, long stride, 
 __global__ void __launch_bounds__(256)
 fc_finish_kernel(const float* __restrict__ partial, int n_splits, long stride, int B, int D,
                  int l2_normalize, float eps, float* __restrict__ emb) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;

@@ -76,6 +76,30 @@ inline bool attr_needed(bool (&done)[64]) {
   return true;
 }
 
+// Programmatic dependent launch (sd_ptx.cuh: pdl_wait / pdl_trigger): while this flag is set, launch_pdl()
+// adds cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's prologue overlaps its predecessor's
+// tail.  ecapa.cu sets it around the trunk (every kernel there calls pdl_wait before touching global memory).
+inline bool& pdl_flag() {
+  static thread_local bool on = false;
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_flag() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int num_sms() {
   static int n = 0;
   if (!n) {
@@ -98,9 +122,9 @@ inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
   const int tiles = P.num_m_blocks * P.num_n_blocks * (P.k_splits > 1 ? P.k_splits : 1);
   if (tiles <= 0) return SD_OK;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<EPI, MAX_BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(P);
+  cudaError_t e = launch_pdl(gemm_tc_kernel<EPI, MAX_BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, P);
   count_launch();
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   static const bool sync_debug = getenv("SD_SYNC_DEBUG") != nullptr;  // localise a faulting launch
   if (e == cudaSuccess && sync_debug) e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess)
@@ -160,13 +184,15 @@ inline int launch_gemm_2sm(const GemmParams& P, cudaStream_t stream) {
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_flag() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI_TDNN>, P);
   count_launch();
   static const bool sync_debug = getenv("SD_SYNC_DEBUG") != nullptr;

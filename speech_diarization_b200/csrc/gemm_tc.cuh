@@ -1035,7 +1035,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   GemmCtx c;
   PipeState ps;
+  pdl_trigger();
   gemm_setup<EPI, MAX_BN>(smem, c);
+  pdl_wait();   // barriers, TMEM and descriptors are set up under the previous kernel's tail
   gemm_run<EPI, MAX_BN>(P, c, ps);
   gemm_teardown(c);
 }
@@ -1079,6 +1081,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
   using Cfg = Cfg2sm;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  pdl_trigger();
   uint8_t* const stage_out = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
   float* const epi_sp = reinterpret_cast<float*>(stage_out + Cfg::OUT_STAGE_BYTES);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(stage_out + Cfg::OUT_STAGE_BYTES + Cfg::EPI_BYTES);
@@ -1114,6 +1117,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above ran under the previous kernel's tail (programmatic dependent launch)
 
   const int m_units = (P.num_m_blocks + 1) / 2;
   const int num_tiles = m_units * P.num_n_blocks;

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(R2_THREADS, 2)
 res2net_fused_kernel(const __grid_constant__ Res2Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  pdl_trigger();
   uint8_t* const abuf = smem;
   uint8_t* const wring = smem + R2_A_BYTES;
   uint8_t* const ystage = wring + R2_WSLOTS * R2_WBOX;
@@ -111,6 +112,7 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // set-up above overlaps the previous kernel's tail (programmatic dependent launch)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer

@@ -253,6 +253,15 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor
+// in the stream is still running: pdl_trigger() lets the NEXT kernel begin launching (its CTAs become resident
+// as this grid's CTAs retire and run their prologue), pdl_wait() blocks until the PREVIOUS grid has completed
+// and its writes are visible.  Every global read or write of such a kernel comes after pdl_wait().  Both are
+// no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for a K-major operand tile stored as
 // [rows][64 x 16-bit] with the 128-byte swizzle TMA writes (CU_TENSOR_MAP_SWIZZLE_128B):

@@ -10,4 +10,4 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.jso
 python tools/ncu_target.py > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/ncu_target.py > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-bash tools/ncu_gemm.sh mfa tdnn2 r2f se pool
+bash tools/ncu_gemm.sh mfa tdnn2 r2f att pool fbank se aff ahc post

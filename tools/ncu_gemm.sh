@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu --set full captures of the GEMM instantiations (second forward of tools/ncu_target.py).
 # <1,256> launches per forward: block0, (tdnn1, tdnn2) x3, mfa  -> second forward = indices 8..15
-# usage: tools/ncu_gemm.sh [mfa] [tdnn2] [res] [pool] [fbank] [ahc] [aff]
+# usage: tools/ncu_gemm.sh [mfa] [tdnn2] [r2f] [att] [pool] [fbank] [se] [ahc] [aff] [post]
 set -x
 mkdir -p gpurun_out
 python tools/ncu_target.py > gpurun_out/ncu_plain.log 2>&1 || { tail -5 gpurun_out/ncu_plain.log; exit 1; }
@@ -17,7 +17,8 @@ case $what in
  fbank) ncu $N -k 'regex:fbank_frames' -s 1 -c 1 -o gpurun_out/prof_fbank python tools/ncu_target.py > gpurun_out/ncu_fbank.log 2>&1;;
  ahc)   ncu $N -k 'regex:ahc_rounds' -c 1 -o gpurun_out/prof_ahc python tools/ncu_target.py > gpurun_out/ncu_ahc.log 2>&1;;
  aff)   ncu $N -k 'regex:gemm_tc_kernel<\(int\)3' -c 1 -o gpurun_out/prof_aff python tools/ncu_target.py > gpurun_out/ncu_aff.log 2>&1;;
- se)    ncu $N -k 'regex:se_mlp|se_apply|time_mean' -s 6 -c 4 -o gpurun_out/prof_se python tools/ncu_target.py > gpurun_out/ncu_se.log 2>&1;;
+ se)    ncu $N -k 'regex:colstats_finish|se_hidden|se_scale|se_apply' -s 12 -c 4 -o gpurun_out/prof_se python tools/ncu_target.py > gpurun_out/ncu_se.log 2>&1;;
+ post)  ncu $N -k 'regex:viterbi_forward|cohort_topk|jacobi_kernel|gram_kernel|hysteresis|mask_segments' -c 7 -o gpurun_out/prof_post python tools/ncu_target.py > gpurun_out/ncu_post.log 2>&1;;
 esac
 echo "$what rc=$?"
 done
