@@ -122,7 +122,7 @@ inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
   const int tiles = P.num_m_blocks * P.num_n_blocks * (P.k_splits > 1 ? P.k_splits : 1);
   if (tiles <= 0) return SD_OK;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  cudaError_t e = launch_pdl(gemm_tc_kernel<EPI, MAX_BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, P);
+  cudaError_t e = launch_pdl(gemm_tc_kernel<EPI, MAX_BN>, dim3(grid), dim3(gemm_threads_of(EPI)), Cfg::SMEM_BYTES, stream, P);
   count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();
   static const bool sync_debug = getenv("SD_SYNC_DEBUG") != nullptr;  // localise a faulting launch

@@ -44,6 +44,12 @@ constexpr int GEMM_THREADS = 320;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
+// Epilogue warps per CTA, per epilogue kind.  The attentive-pooling epilogue (EPI_POOL) does ~14 instructions of
+// softmax / moment arithmetic per frame-channel; POOL_EPI_WARPS = 16 (four warps per TMEM lane quarter, 576
+// threads) was built and measured: the launch got SLOWER (0.27-0.29 -> 0.355 ms), so 8 stays.
+constexpr int POOL_EPI_WARPS = 8;
+__host__ __device__ constexpr int epi_warps_of(int epi) { return epi == 2 /*EPI_POOL*/ ? POOL_EPI_WARPS : EPI_WARPS; }
+__host__ __device__ constexpr int gemm_threads_of(int epi) { return 64 + 32 * epi_warps_of(epi); }
 
 enum { EPI_F32 = 0, EPI_TDNN = 1, EPI_POOL = 2, EPI_AFF = 3, EPI_ATT = 4, EPI_CONV3 = 5 };
 // EPI_CONV3 = EPI_TDNN's epilogue behind a different operand path for the small dilated k=3 convolutions
@@ -166,8 +172,9 @@ struct GemmCfg {
 };
 
 // ------------------------------------------------------------------ epilogues
+template <int THREADS = EPI_THREADS>
 __device__ __forceinline__ void epi_named_barrier() {
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
 }
 
 // raw f32
@@ -488,7 +495,7 @@ struct PoolState {
 // three running sums use two independent accumulators each.  The generic path below (two TMEM reads,
 // one wait per 16 columns, per-element edge tests) was issue- and latency-bound: 17 instructions and
 // ~70 cycles per element per warp in ncu (profiles/r01_ncu_head.txt).
-template <int NCH>
+template <int NCH, int NP>   // NP = epilogue warps per lane quarter; this warp owns runs part, part + NP, ...
 __device__ __forceinline__ void pool_chunks_regs(const GemmParams& P, uint32_t tbase, int half,
                                                  const uint8_t* hchunk, int c16, float g, PoolState& st) {
   const EpiParams& E = P.epi;
@@ -496,14 +503,14 @@ __device__ __forceinline__ void pool_chunks_regs(const GemmParams& P, uint32_t t
   uint32_t v[NCH][16];
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
-    const int c0 = (2 * i + half) * 16;
+    const int c0 = (NP * i + half) * 16;
     if (c0 < P.n_tile) tmem_ld16(tbase + c0, v[i]);
   }
   tmem_ld_wait();
   float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
-    const int t0 = (2 * i + half) * 16 - E.H;  // frame index of the run's first column
+    const int t0 = (NP * i + half) * 16 - E.H;  // frame index of the run's first column
     if (!(t0 >= 0 && t0 + 16 <= E.T)) {        // run touches the halo / padding (warp-uniform)
 #pragma unroll
       for (int j = 0; j < 16; ++j)
@@ -517,7 +524,7 @@ __device__ __forceinline__ void pool_chunks_regs(const GemmParams& P, uint32_t t
   float se[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
-    const int c0 = (2 * i + half) * 16;
+    const int c0 = (NP * i + half) * 16;
     const int t0 = c0 - E.H;
     if (c0 < P.n_tile) {
       float xv[16];
@@ -549,7 +556,9 @@ __device__ __forceinline__ void pool_chunks_regs(const GemmParams& P, uint32_t t
 
 __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, int n_blk, int sub,
                                               uint32_t tmem_acc, int quarter, int half, int lane,
-                                              const uint8_t* hbuf, float4* xchg, PoolState& st, float g) {
+                                              uint8_t* hbuf, PoolState& st, float g) {
+  constexpr int NP = POOL_EPI_WARPS / 4;          // `half` is the warp's part index 0 .. NP-1
+  constexpr int PT = POOL_EPI_WARPS * 32;
   const EpiParams& E = P.epi;
   const int chl = quarter * 32 + lane;  // channel within the tile
   const int ch = m_blk * BM + chl;
@@ -561,14 +570,15 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
   const uint8_t* hchunk = hbuf + (chl >> 6) * (P.n_tile * 128) + (chl & 7) * 2;
   const int c16 = (chl & 63) >> 3;
   float se, s1, s2;
-  if (P.n_sub == 1 && P.n_tile <= 160) {
-    pool_chunks_regs<5>(P, tbase, half, hchunk, c16, g, st);
+  constexpr int NCH = NP == 2 ? 5 : 3;            // 16-column runs a warp keeps in registers (windows <= 1.5 s)
+  if (P.n_sub == 1 && P.n_tile <= NP * NCH * 16) {
+    pool_chunks_regs<NCH, NP>(P, tbase, half, hchunk, c16, g, st);
     se = st.se; s1 = st.s1; s2 = st.s2;
   } else {
     // this warp's share of the frames: 16-column chunks  half, half+2, ...
     // pass 1: max over this chunk's interior frames
     float cm = -INFINITY;
-    for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
+    for (int c0 = half * 16; c0 < P.n_tile; c0 += NP * 16) {
       uint32_t v[16];
       tmem_ld16(tbase + c0, v);
       tmem_ld_wait();
@@ -594,7 +604,7 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
     // pass 2: softmax-weighted first/second moments about the global mean g
     const float mxs = (st.mx == -INFINITY) ? 0.f : st.mx * LOG2E;  // nothing interior seen yet
     se = st.se; s1 = st.s1; s2 = st.s2;
-    for (int c0 = half * 16; c0 < P.n_tile; c0 += 32) {
+    for (int c0 = half * 16; c0 < P.n_tile; c0 += NP * 16) {
       uint32_t v[16];
       tmem_ld16(tbase + c0, v);
       float xv[16];
@@ -632,17 +642,29 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
   st.s1 = s1;
   st.s2 = s2;
   if (sub + 1 < P.n_sub) return;  // more time chunks of this utterance follow
-  // last chunk: combine the two column halves (half 1 -> shared -> half 0) and finish
-  if (half == 1) xchg[chl] = make_float4(st.mx, se, s1, s2);
-  epi_named_barrier();
+  // last chunk: combine the NP column parts (parts 1.. -> shared -> part 0) and finish.  The exchange area is
+  // the h tile this epilogue has just finished reading: the producer cannot refill it before all the
+  // epilogue warps have arrived on its "empty" barrier, which part 0 does only after reading the exchange.
+  float4* xchg = reinterpret_cast<float4*>(hbuf);
+  epi_named_barrier<PT>();            // every warp is done with the h tile
+  if (half > 0) xchg[(half - 1) * BM + chl] = make_float4(st.mx, se, s1, s2);
+  epi_named_barrier<PT>();
   if (half == 0) {
-    const float4 o = xchg[chl];
-    const float M = fmaxf(st.mx, o.x);
+    float M = st.mx;
+#pragma unroll
+    for (int q = 0; q < NP - 1; ++q) M = fmaxf(M, xchg[q * BM + chl].x);
     const float fa = (st.mx == -INFINITY) ? 0.f : ex2_approx((st.mx - M) * LOG2E);
-    const float fb = (o.x == -INFINITY) ? 0.f : ex2_approx((o.x - M) * LOG2E);
-    se = se * fa + o.y * fb;
-    s1 = s1 * fa + o.z * fb;
-    s2 = s2 * fa + o.w * fb;
+    se *= fa;
+    s1 *= fa;
+    s2 *= fa;
+#pragma unroll
+    for (int q = 0; q < NP - 1; ++q) {
+      const float4 o = xchg[q * BM + chl];
+      const float fb = (o.x == -INFINITY) ? 0.f : ex2_approx((o.x - M) * LOG2E);
+      se = fmaf(o.y, fb, se);
+      s1 = fmaf(o.z, fb, s1);
+      s2 = fmaf(o.w, fb, s2);
+    }
     if (chv) {
       const float inv = 1.f / se;
       const float m1 = s1 * inv;
@@ -657,7 +679,8 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
       }
     }
   }
-  epi_named_barrier();  // xchg may be overwritten by the next tile
+  // generic-proxy accesses to the h buffer are ordered before the TMA refill that follows the empty barrier
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   st = PoolState();
 }
 
@@ -767,9 +790,9 @@ __device__ __forceinline__ void gemm_setup(uint8_t* smem, GemmCtx& c) {
   c.empty_bar = bars + Cfg::STAGES;         // [STAGES]
   c.tfull_bar = bars + 2 * Cfg::STAGES;     // [2]
   c.tempty_bar = c.tfull_bar + 2;           // [2]
-  c.hfull_bar = c.tempty_bar + 2;           // [2]  EPI_POOL: staged h tile landed
-  c.hempty_bar = c.hfull_bar + 2;           // [2]  EPI_POOL: epilogue done with it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.hempty_bar + 2);
+  c.hfull_bar = c.tempty_bar + 2;           // [3]  EPI_POOL: staged h tile landed
+  c.hempty_bar = c.hfull_bar + 3;           // [3]  EPI_POOL: epilogue done with it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.hempty_bar + 3);
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
   if (c.warp == 0) {
@@ -780,9 +803,11 @@ __device__ __forceinline__ void gemm_setup(uint8_t* smem, GemmCtx& c) {
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&c.tfull_bar[s], 1);
-        mbar_init(&c.tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
+        mbar_init(&c.tempty_bar[s], epi_warps_of(EPI));  // one arrive per epilogue warp
+      }
+      for (int s = 0; s < 3; ++s) {
         mbar_init(&c.hfull_bar[s], 1);
-        mbar_init(&c.hempty_bar[s], EPI_WARPS);
+        mbar_init(&c.hempty_bar[s], epi_warps_of(EPI));
       }
       fence_barrier_init();
     }
@@ -821,6 +846,9 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
   uint8_t* const stage_out = bres + Cfg::BRES_BYTES;                  // EPI_TDNN/ATT/AFF output staging (64 KB)
   float* const epi_sp = reinterpret_cast<float*>(epi_region);  // EPI_TDNN: per-column constants
   const uint32_t hbuf_bytes = 2u * static_cast<uint32_t>(P.n_tile) * 128u;  // EPI_POOL: one h tile
+  // h tiles in flight: three when they fit the region sized for two 256-frame tiles (windows <= 1.6 s), so the
+  // tile after next is already streaming from HBM while the epilogue works
+  const int h_bufs = (EPI == EPI_POOL && 3u * hbuf_bytes <= 2u * 2u * MAX_BN * 128u) ? 3 : 2;
   const int warp = c.warp, lane = c.lane;
   const int k_splits = P.k_splits < 1 ? 1 : P.k_splits;
   const int k_per = (P.num_kiters + k_splits - 1) / k_splits;
@@ -878,7 +906,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
             uint8_t* hb = epi_region + ps.hs * hbuf_bytes;
             tma_load_2d(hb, &P.tmapH, &c.hfull_bar[ps.hs], m_blk * BM, b_row);
             tma_load_2d(hb + hbuf_bytes / 2, &P.tmapH, &c.hfull_bar[ps.hs], m_blk * BM + BK, b_row);
-            if (++ps.hs == 2) { ps.hs = 0; ps.hphase ^= 1; }
+            if (++ps.hs == h_bufs) { ps.hs = 0; ps.hphase ^= 1; }
           }
           for (int k = k_begin; k < k_end; ++k) {
             mbar_wait(&c.empty_bar[ps.stage], ps.phase ^ 1);
@@ -961,7 +989,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
   } else {
     // ---------------------------------------------------------------- epilogue
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;    // which half of the tile's column chunks it handles
+    const int half = (warp - 2) >> 2;    // which part of the tile's column chunks it handles (0..1; EPI_POOL 0..3)
     const int et = threadIdx.x - 64;
     int last_n_blk = -1;
     PoolState pool_state;
@@ -1002,11 +1030,11 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       }
       if (EPI == EPI_POOL) {
         mbar_wait(&c.hfull_bar[ps.hs], ps.hphase);
-        epilogue_pool(P, m_blk, n_blk, sub, acc, quarter, half, lane, epi_region + ps.hs * hbuf_bytes,
-                      reinterpret_cast<float4*>(epi_region + 2 * 2 * MAX_BN * 128), pool_state, pool_g);
+        epilogue_pool(P, m_blk, n_blk, sub, acc, quarter, half, lane, epi_region + ps.hs * hbuf_bytes, pool_state,
+                      pool_g);
         __syncwarp();
         if (lane == 0) mbar_arrive(&c.hempty_bar[ps.hs]);
-        if (++ps.hs == 2) { ps.hs = 0; ps.hphase ^= 1; }
+        if (++ps.hs == h_bufs) { ps.hs = 0; ps.hphase ^= 1; }
       }
       if (EPI == EPI_AFF) {
         epi_named_barrier();  // previous tile's staging has been written out
@@ -1030,7 +1058,7 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
 }
 
 template <int EPI, int MAX_BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads_of(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   GemmCtx c;
