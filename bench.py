@@ -181,7 +181,7 @@ def run_reference_arm(args, rank: int) -> None:
                              "sample": f"{per_step} windows x {args.steps} steps, oracle/ecapa_oracle.py"},
             "e2e": {"value": val, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------- AHC leg
@@ -348,7 +348,29 @@ def load_peaks():
 
 
 # ----------------------------------------------------------------------------------- main arm
+_JSON_FD = None
+
+
+def _claim_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    fd 1 under torchrun), so the process's fd 1 is pointed at stderr for the whole run and the JSON line goes
+    to a private duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main() -> None:
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -498,7 +520,7 @@ def main() -> None:
             line["dense_pass"] = dense_pass_leg(enc, audio, device)
             line["ahc"] = ahc_leg(device, with_cpu=not args.no_cpu_baseline)
             line["post"] = post_leg(device, with_cpu=not args.no_cpu_baseline)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

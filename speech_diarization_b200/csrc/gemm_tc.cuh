@@ -521,7 +521,7 @@ __device__ __forceinline__ void pool_chunks_regs(const GemmParams& P, uint32_t t
   }
   const float mx = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
   const float mxs = (mx == -INFINITY) ? 0.f : mx * LOG2E;
-  float se[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+  float se[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c0 = (NP * i + half) * 16;
@@ -541,17 +541,17 @@ __device__ __forceinline__ void pool_chunks_regs(const GemmParams& P, uint32_t t
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float e = ex2_approx(fmaf(__uint_as_float(v[i][j]), LOG2E, -mxs));
-        se[j & 1] += e;
+        se[j & 3] += e;
         const float ex = e * xv[j];
-        s1[j & 1] += ex;
-        s2[j & 1] = fmaf(ex, xv[j], s2[j & 1]);
+        s1[j & 3] += ex;
+        s2[j & 3] = fmaf(ex, xv[j], s2[j & 3]);
       }
     }
   }
   st.mx = mx;
-  st.se = se[0] + se[1];
-  st.s1 = s1[0] + s1[1];
-  st.s2 = s2[0] + s2[1];
+  st.se = (se[0] + se[1]) + (se[2] + se[3]);
+  st.s1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+  st.s2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
 }
 
 __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, int n_blk, int sub,
