@@ -5,15 +5,22 @@ reaches through ``EncoderClassifier.encode_batch`` (call sites
 ``speech_encode.py:77``, ``ecapa_annote.py:22``, ``diar_diag.py:169``):
 speechbrain ``Fbank`` -> ``InputNormalization(sentence)`` -> ``ECAPA_TDNN``.
 
-PARITY UNPINNED for this file: speechbrain is a third-party dependency of the
+PARITY PARTLY PINNED for this file: speechbrain is a third-party dependency of the
 reference that is absent from /root/reference and not installable here (no
 version pin exists in the reference tree either; the import path
-``speechbrain.inference`` implies >= 1.0).  The topology below restates
-speechbrain's published ``lobes/models/ECAPA_TDNN.py`` and
-``processing/features.py`` from SURVEY.md Appendix A; it is cross-checked only by
-its parameter count (20 767 552 == the published embedding_model.ckpt size / 4)
-and by the state-dict key names, which mirror speechbrain's so that a real
-checkpoint can validate it later.
+``speechbrain.inference`` implies >= 1.0), so the reference's own ECAPA cannot be
+run.  What IS pinned: the trunk topology (TDNN / Res2Net / SE / attentive
+statistics pooling / fc wiring, reflect 'same' padding, pooled-std epsilon) is
+checked bit for bit against an installed third-party port of speechbrain's
+``lobes/models/ECAPA_TDNN.py`` — transformers' ``ECAPA_TimeDelayNet`` (Qwen2.5-Omni
+token2wav), which is that model minus the BatchNorm layers
+(tests/golden/make_ecapa_hf_golden.py, tests/test_oracle_golden.py).  What is
+still recalled from SURVEY.md Appendix A: where the BatchNorms sit (after the
+ReLU inside every TDNN block; ``asp_bn`` before ``fc``) and the Fbank /
+InputNormalization front end (``processing/features.py``).  Also cross-checked:
+the parameter count (20 767 552 == the published embedding_model.ckpt size / 4)
+and the state-dict key names, which mirror speechbrain's so that a real
+checkpoint can validate the rest later.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this module.

@@ -11,6 +11,9 @@ patched to no-ops so the reference's own torchaudio arithmetic runs on CPU.
 post_ref.npz holds outputs of diar_diag.asnorm_scores / viterbi_hmm and of
 vad.hysteresis_binarize / morph_open_close / mask_to_segments, again the reference's own functions.
 
+ecapa_hf_ref.npz (third-party pin of the ECAPA-TDNN trunk topology) is made by make_ecapa_hf_golden.py, a
+separate script because the stub modules installed here confuse transformers' optional-dependency probes.
+
 Run:  python tests/golden/make_golden.py        (needs /root/reference; not run on the GPU box)
 """
 import hashlib

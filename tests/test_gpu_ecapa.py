@@ -189,3 +189,25 @@ def test_unsupported_and_bad_arguments(encoder):
     with pytest.raises(ValueError):
         encoder.embed_device(torch.zeros(100, device="cuda"), 100, 1, 100)
     assert encoder.embed_device(torch.zeros(0, device="cuda"), 1, 0, 24000).shape == (0, 192)
+
+
+def test_trunk_matches_transformers_ecapa_golden():
+    """CUDA trunk against the third-party golden (transformers' ECAPA_TimeDelayNet, tests/golden/ecapa_hf_ref.npz):
+    the oracle's seed-0 conv weights with every BatchNorm an exact identity.  Gate: 1 - cos <= 1e-4."""
+    from conftest import golden
+    from oracle import ecapa_oracle
+    from speech_diarization_b200 import speech_encode
+    g = golden("ecapa_hf_ref.npz")
+    model = ecapa_oracle.make_random_ecapa(0)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.weight.data.fill_(1); m.bias.data.zero_(); m.running_mean.zero_(); m.running_var.fill_(1.0 - m.eps)
+    enc = speech_encode.EcapaEncoderB200(model.state_dict(), device="cuda:0", max_batch=4, max_samples=16000)
+    try:
+        got = enc.forward_feats(torch.from_numpy(g["feats"])).cpu()
+    finally:
+        enc.close()
+    ref = torch.from_numpy(g["emb"])
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=1)
+    assert float((1 - cos).max()) <= 1e-4, float((1 - cos).max())
+    assert float((got - ref).abs().max()) <= 2e-3 * float(ref.abs().max())

@@ -236,3 +236,23 @@ def test_post_oracle_pipeline_matches_reference_functions(tag, wh, asn, vbx, thr
     np.testing.assert_array_equal(final, g[f"pipe_{tag}_final"])
     assert co.same_partition(labels, g["pipe_true"])
     assert merged[0][0] == segs[0][0] and merged[-1][1] == segs[-1][1] and len(merged) >= 20
+
+
+# ------------------------------------------------------------------ ECAPA-TDNN trunk vs an installed third party
+def _neutral_bn(model):
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.weight.data.fill_(1); m.bias.data.zero_(); m.running_mean.zero_(); m.running_var.fill_(1.0 - m.eps)
+    return model
+
+
+def test_ecapa_oracle_trunk_matches_transformers_ecapa_golden():
+    """tests/golden/ecapa_hf_ref.npz = transformers' ECAPA_TimeDelayNet (speechbrain's ECAPA_TDNN without the
+    BatchNorms) run with the oracle's seed-0 conv weights (make_ecapa_hf_golden.py).  The oracle with identity
+    BatchNorms reproduces it bit for bit: its conv / Res2Net / SE / ASP / fc wiring is pinned to third-party code."""
+    g = golden("ecapa_hf_ref.npz")
+    model = _neutral_bn(eo.make_random_ecapa(0))
+    with torch.inference_mode():
+        out = model(torch.from_numpy(g["feats"])).squeeze(1).numpy()
+    np.testing.assert_array_equal(out, g["emb"])
+    assert out.shape == (3, 192) and np.abs(out).max() > 0.05
