@@ -77,7 +77,9 @@ def synth_audio(seconds: int, n_speakers: int, seed: int, device) -> torch.Tenso
 
 # ---------------------------------------------------------------------------- clocks sampling
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread every 5 ms (the timed
+    region is ~150 ms, too short for an `nvidia-smi -lms` child to start up reliably), falling back to the
+    recipe's nvidia-smi query loop when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -86,8 +88,31 @@ class ClockSampler:
         self.idx = gpu_index
         self.lines: list[str] = []
         self.proc = None
+        self.nvml = None
+        self.samples: list[tuple[float, int]] = []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        if ids and self.idx < len(ids) and ids[self.idx].strip().isdigit():
+            return int(ids[self.idx])
+        return self.idx
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, h)
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "25", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
@@ -95,11 +120,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                     int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                                     if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons")
+                                     else int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            pynvml = self.nvml[0]
+            bits = {"hw_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            sm = [c for c, _ in self.samples]
+            reasons = sorted(name for name, bit in bits.items() if any(r & bit for _, r in self.samples))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -117,7 +166,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------- CPU baseline

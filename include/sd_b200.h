@@ -99,6 +99,15 @@ int sd_ecapa_plan_destroy(SdEcapaPlan* plan);
 int sd_ecapa_embed(SdEcapaPlan* plan, const float* wav_dev, long wav_stride, int B, int n_samples,
                    int l2_normalize, float* emb_dev, void* stream);
 
+/* The same from HOST memory — the call behind ecapa_encode_batch(np.ndarray) (speech_encode.py:73-78) and
+ * `emb = encode_batch(wav).cpu().numpy()`: wav_host / emb_host are host pointers (pinned or pageable), window
+ * b = wav_host[b * wav_stride : b * wav_stride + n_samples], emb_host [B, 192] f32.  The host->device copy is
+ * issued in four chunks on a plan-owned copy stream and each chunk's fbank kernels start as soon as it has
+ * landed, so all but the first quarter of the upload runs under compute; the embeddings are copied back and
+ * the stream is synchronised before returning (the reference's call ends with the same implicit sync). */
+int sd_ecapa_embed_host(SdEcapaPlan* plan, const float* wav_host, long wav_stride, int B, int n_samples,
+                        int l2_normalize, float* emb_host, void* stream);
+
 /* Same trunk from precomputed features feats_dev [B, T, 80] f32 (already
  * normalised); used by the parity tests to isolate the trunk. */
 int sd_ecapa_forward_feats(SdEcapaPlan* plan, const float* feats_dev, int B, int T,

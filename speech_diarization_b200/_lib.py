@@ -29,6 +29,7 @@ SIGNATURES = {
     "sd_ecapa_plan_create": (c_int, [POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_int, c_int, POINTER(c_void_p)]),
     "sd_ecapa_plan_destroy": (c_int, [c_void_p]),
     "sd_ecapa_embed": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sd_ecapa_embed_host": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sd_ecapa_forward_feats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sd_ecapa_debug_fetch": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int), c_void_p]),
     "sd_ecapa_profile": (c_int, [c_void_p, c_int]),

@@ -111,6 +111,15 @@ struct SdEcapaPlan {
   bool use_conv3 = true;   // SD_ECAPA_CONV3=0: Res2Net convs through the generic tap-per-k-iteration path
   bool use_graph = true;   // SD_ECAPA_GRAPH=0 disables CUDA-graph replay of the trunk
   cudaStream_t cap_stream = nullptr;
+  // sd_ecapa_embed_host: device staging of the caller's host audio, a copy stream and per-chunk events so the
+  // host->device copy of chunk c+1 runs under the fbank kernels of chunk c
+  float* h2d_buf = nullptr;
+  size_t h2d_cap = 0;       // samples
+  float* emb_stage = nullptr;
+  int emb_cap = 0;          // windows
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[8] = {};
+  cudaEvent_t start_ev = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   int forwards_profiled = 0;
@@ -764,6 +773,12 @@ extern "C" int sd_ecapa_plan_destroy(SdEcapaPlan* p) {
   cudaDeviceSynchronize();
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+  for (cudaEvent_t e : p->copy_ev)
+    if (e) cudaEventDestroy(e);
+  if (p->start_ev) cudaEventDestroy(p->start_ev);
+  if (p->h2d_buf) cudaFree(p->h2d_buf);
+  if (p->emb_stage) cudaFree(p->emb_stage);
   for (auto& kv : p->programs)
     if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
   for (void* d : p->allocs) cudaFree(d);
@@ -784,6 +799,72 @@ extern "C" int sd_ecapa_embed(SdEcapaPlan* p, const float* wav_dev, long wav_str
   SD_TRY(fbank_launch(wav_dev, wav_stride, B, n_samples, SD_FBANK_SPEECHBRAIN, 1, p->raw, nullptr,
                       p->feats, pr->Tp, HALO, st));
   return run_trunk(p, *pr, l2_normalize, emb_dev, st);
+}
+
+extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long wav_stride, int B, int n_samples,
+                                   int l2_normalize, float* emb_host, void* stream) {
+  if (!p || !wav_host || !emb_host) return fail(SD_ERR_ARG, "sd_ecapa_embed_host: NULL argument");
+  if (n_samples < 400 || wav_stride < 1)
+    return fail(SD_ERR_ARG, "sd_ecapa_embed_host: n_samples=%d stride=%ld", n_samples, wav_stride);
+  const int T = 1 + n_samples / 160;
+  SD_TRY(check_shape(p, B, T));
+  Program* pr = nullptr;
+  SD_TRY(build_program(p, B, T, &pr));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  constexpr int NCH = 4;
+  if (!p->copy_stream) {
+    SD_CUDA_OK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int c = 0; c < NCH; ++c) SD_CUDA_OK(cudaEventCreateWithFlags(&p->copy_ev[c], cudaEventDisableTiming));
+    SD_CUDA_OK(cudaEventCreateWithFlags(&p->start_ev, cudaEventDisableTiming));
+  }
+  if (B > p->emb_cap) {
+    SD_CUDA_OK(cudaStreamSynchronize(st));
+    if (p->emb_stage) cudaFree(p->emb_stage);
+    p->emb_stage = nullptr;
+    p->emb_cap = 0;
+    SD_CUDA_OK(cudaMalloc(&p->emb_stage, static_cast<size_t>(B) * EMB * sizeof(float)));
+    p->emb_cap = B;
+  }
+  const size_t span = static_cast<size_t>(B - 1) * wav_stride + n_samples;
+  if (span > p->h2d_cap) {
+    SD_CUDA_OK(cudaStreamSynchronize(st));
+    if (p->h2d_buf) cudaFree(p->h2d_buf);
+    p->h2d_buf = nullptr;
+    p->h2d_cap = 0;
+    SD_CUDA_OK(cudaMalloc(&p->h2d_buf, span * sizeof(float)));
+    p->h2d_cap = span;
+  }
+  // the staging buffer may still be read by work queued earlier on `st`
+  SD_CUDA_OK(cudaEventRecord(p->start_ev, st));
+  SD_CUDA_OK(cudaStreamWaitEvent(p->copy_stream, p->start_ev, 0));
+  mark(p, st);  // start of fbank
+  const int chunks = B >= 64 ? NCH : 1;
+  size_t copied = 0;  // samples of the span already queued (windows overlap when stride < n)
+  for (int c = 0; c < chunks; ++c) {
+    const int b0 = static_cast<int>(static_cast<long>(B) * c / chunks);
+    const int b1 = static_cast<int>(static_cast<long>(B) * (c + 1) / chunks);
+    if (b1 <= b0) continue;
+    if (wav_stride <= n_samples) {
+      const size_t end = static_cast<size_t>(b1 - 1) * wav_stride + n_samples;
+      SD_CUDA_OK(cudaMemcpyAsync(p->h2d_buf + copied, wav_host + copied, (end - copied) * sizeof(float),
+                                 cudaMemcpyHostToDevice, p->copy_stream));
+      copied = end;
+    } else {   // gaps between windows belong to the caller: copy the windows only
+      SD_CUDA_OK(cudaMemcpy2DAsync(p->h2d_buf + static_cast<size_t>(b0) * wav_stride, wav_stride * sizeof(float),
+                                   wav_host + static_cast<size_t>(b0) * wav_stride, wav_stride * sizeof(float),
+                                   static_cast<size_t>(n_samples) * sizeof(float), b1 - b0, cudaMemcpyHostToDevice,
+                                   p->copy_stream));
+    }
+    SD_CUDA_OK(cudaEventRecord(p->copy_ev[c], p->copy_stream));
+    SD_CUDA_OK(cudaStreamWaitEvent(st, p->copy_ev[c], 0));
+    SD_TRY(fbank_launch(p->h2d_buf + static_cast<size_t>(b0) * wav_stride, wav_stride, b1 - b0, n_samples,
+                        SD_FBANK_SPEECHBRAIN, 1, p->raw + static_cast<size_t>(b0) * T * 80, nullptr,
+                        p->feats + static_cast<size_t>(b0) * pr->Tp * FEAT_P, pr->Tp, HALO, st));
+  }
+  SD_TRY(run_trunk(p, *pr, l2_normalize, p->emb_stage, st));
+  SD_CUDA_OK(cudaMemcpyAsync(emb_host, p->emb_stage, static_cast<size_t>(B) * EMB * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SD_CUDA_OK(cudaStreamSynchronize(st));
+  return SD_OK;
 }
 
 extern "C" int sd_ecapa_forward_feats(SdEcapaPlan* p, const float* feats_dev, int B, int T,

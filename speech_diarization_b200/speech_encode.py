@@ -137,6 +137,31 @@ class EcapaEncoderB200:
                                                     out.data_ptr() + 4 * EMB_DIM * b0, st), "sd_ecapa_embed")
         return out
 
+    def embed_host(self, wavs: np.ndarray, wav_stride: int, n_windows: int, n_samples: int,
+                   l2_normalize: bool = False) -> np.ndarray:
+        """Embeddings of windows addressed in place in a HOST f32 buffer (numpy, contiguous span): the upload is
+        chunked and overlapped with the fbank kernels inside the C call (sd_ecapa_embed_host).  Returns
+        [n_windows, 192] f32 numpy; synchronous like the reference's `.cpu().numpy()`."""
+        B, n = int(n_windows), int(n_samples)
+        out = np.empty((B, EMB_DIM), dtype=np.float32)
+        if B == 0:
+            return out
+        if n < 400:
+            raise ValueError(f"windows of {n} samples are shorter than one 25 ms analysis frame")
+        tp = self._tp(1 + n // _HOP)
+        if tp > self._max_rows:
+            self._make_plan(1, n)
+        per_call = max(1, self._max_rows // tp)
+        base = wavs.ctypes.data
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr()
+            for b0 in range(0, B, per_call):
+                nb = min(per_call, B - b0)
+                _lib.check(self._lib.sd_ecapa_embed_host(self._plan, base + 4 * b0 * wav_stride, wav_stride, nb, n,
+                                                         int(bool(l2_normalize)), out.ctypes.data + 4 * EMB_DIM * b0, st),
+                           "sd_ecapa_embed_host")
+        return out
+
     def encode_batch(self, wavs: torch.Tensor, wav_lens=None, normalize: bool = False) -> torch.Tensor:
         """EncoderClassifier.encode_batch: [B, n] (or [n]) waveform tensor -> [B, 1, 192] on the
         encoder's device.  wav_lens is accepted for signature compatibility; the reference never
@@ -231,7 +256,14 @@ def ecapa_encode_batch(wavs: np.ndarray) -> np.ndarray:
     encoder = using_ecapa_encoder()
     with torch.inference_mode():
         ov = _overlap_span(wavs) if isinstance(wavs, np.ndarray) else None
-        if ov is not None:
+        host_path = os.environ.get("SD_ECAPA_HOST_PATH", "1") != "0"
+        if ov is not None and host_path:
+            span, hop = ov                                               # windows addressed in place in host memory
+            y = encoder.embed_host(span, hop, wavs.shape[0], wavs.shape[1])
+        elif (host_path and isinstance(wavs, np.ndarray) and wavs.ndim == 2 and wavs.dtype == np.float32
+              and wavs.flags.c_contiguous and wavs.shape[0] > 0):
+            y = encoder.embed_host(wavs, wavs.shape[1], wavs.shape[0], wavs.shape[1])
+        elif ov is not None:
             span, hop = ov
             audio = to_device_f32(span, encoder.device)
             y = encoder.embed_device(audio, hop, wavs.shape[0], wavs.shape[1]).cpu().numpy()

@@ -106,3 +106,29 @@ def test_config5_dense_reassignment_pass_matches_oracle(oracle_model):
         se.register_ecapa_state_dict(None)
     assert [(s.start, s.end, s.spk) for s in segs] == [(s.start, s.end, s.spk) for s in segs_ref]
     assert len(segs) >= 4
+
+
+def test_host_buffer_path_equals_device_path(oracle_model, monkeypatch):
+    """ecapa_encode_batch from host memory (sd_ecapa_embed_host: chunked upload overlapped with fbank) gives
+    bit-identical embeddings to the explicit upload + device path, for overlapping window views, contiguous
+    [B, n] batches, few windows (single chunk) and non-contiguous input (falls back to the torch upload)."""
+    import numpy as np
+    from speech_diarization_b200 import speech_encode, vad
+    from conftest import synth_wave
+    speech_encode.register_ecapa_state_dict(oracle_model.state_dict())
+    try:
+        y = synth_wave(1, 16000 * 30, 5)[0]
+        frames = vad.frame_audio(y, 16000, 1000.0, 250.0)           # 117 overlapping windows (4 upload chunks)
+        dense = np.ascontiguousarray(frames[:70])                    # contiguous [70, 16000]
+        few = frames[:5]                                             # one chunk
+        strided = dense[::2]                                         # not contiguous, not a hop view
+        cases = {"view": frames, "dense": dense, "few": few, "strided": strided}
+        host = {k: speech_encode.ecapa_encode_batch(v) for k, v in cases.items()}
+        monkeypatch.setenv("SD_ECAPA_HOST_PATH", "0")
+        dev = {k: speech_encode.ecapa_encode_batch(v) for k, v in cases.items()}
+        for k in cases:
+            assert host[k].shape == (len(cases[k]), 192) and host[k].dtype == np.float32
+            np.testing.assert_array_equal(host[k], dev[k], err_msg=k)
+        np.testing.assert_array_equal(host["view"][:70], host["dense"])
+    finally:
+        speech_encode.register_ecapa_state_dict(None)
