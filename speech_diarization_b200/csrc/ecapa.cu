@@ -107,6 +107,11 @@ struct SdEcapaPlan {
   bool use_r2fused = true; // SD_ECAPA_R2FUSED=0: Res2Net chain as 7 launches per block instead of one
   bool use_pdl = false;    // SD_ECAPA_PDL=1: programmatic dependent launch between the trunk's kernels (measured
                            // 2 % SLOWER inside the replayed graph: 3.70-3.74 vs 3.64-3.66 ms per step)
+  bool use_tma_out = false; // SD_ECAPA_TMAOUT=1: the cta_group::2 GEMMs of the pointwise layers hand their staged tile to TMA
+                            // tensor stores.  Measured 3 % SLOWER than the per-thread write-out (tdnn1 0.144 -> 0.148 ms): the
+                            // launch is bound by operand ingest next to the store traffic, not by the epilogue threads' time
+  bool use_l2_order = true; // SD_ECAPA_L2ORDER=0: se_apply and the attention GEMM walk the rows in ascending order like
+                            // their producers (tdnn2, MFA) instead of starting with the rows those left in L2
   bool use_colsum = true;  // SD_ECAPA_COLSUM=0: separate passes over the activations for the SE mean and ASP mean/std
   bool use_conv3 = true;   // SD_ECAPA_CONV3=0: Res2Net convs through the generic tap-per-k-iteration path
   bool use_graph = true;   // SD_ECAPA_GRAPH=0 disables CUDA-graph replay of the trunk
@@ -233,6 +238,17 @@ int setup_tdnn_gemm(GemmParams& P, const __half* A, long rows, int a_cols, int l
   return SD_OK;
 }
 
+// Pointwise layer on the cta_group::2 kernel: hand the staged tile to TMA tensor stores (EF_TMA_OUT).  The maps
+// cover exactly the columns this layer owns, so clipping at the tensor bounds replaces the row / column guards.
+int enable_tma_out(SdEcapaPlan* p, GemmParams& P) {
+  if (!p->use_2sm || !p->use_tma_out || (P.epi.flags & EF_REFLECT) || P.n_tile != 256) return SD_OK;
+  EpiParams& E = P.epi;
+  SD_TRY(make_tmap_f16(&P.tmapH, static_cast<__half*>(E.out) + E.out_col_off, E.M_rows, E.N_cols, E.ld_out, BM));
+  if (E.out2 != nullptr) SD_TRY(make_tmap_f16(&P.tmapO2, E.out2, E.M_rows, E.out2_cols, E.ld_out2, BM));
+  E.flags |= EF_TMA_OUT;
+  return SD_OK;
+}
+
 int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   auto key = std::make_pair(B, T);
   auto it = p->programs.find(key);
@@ -266,6 +282,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     pr.tdnn1[b].epi.out2 = p->v;
     pr.tdnn1[b].epi.ld_out2 = C1;
     pr.tdnn1[b].epi.out2_cols = SUB;
+    SD_TRY(enable_tma_out(p, pr.tdnn1[b]));
     // Res2Net chain: y_i = TDNN_i(x_i + y_{i-1}), i = 1..7 (y_0 = x_0 passes through)
     for (int i = 1; i <= 7; ++i) {
       const __half* A = i == 1 ? p->u : p->s[i & 1];
@@ -316,6 +333,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
                            p->w, C1, 0, 0, p->use_mc || p->use_2sm));
     pr.colsum_ok = p->use_colsum && pr.Tp >= 128;
     if (pr.colsum_ok) pr.tdnn2[b].epi.colsum = p->cs_se;
+    SD_TRY(enable_tma_out(p, pr.tdnn2[b]));
   }
   SD_TRY(setup_tdnn_gemm(pr.mfa, p->cat, R, C3, C3, p->wmfa, C3, C3, 256, C3, 1, 1, 0, pr, p->h, C3,
                          0, 0, p->use_mc || p->use_2sm));
@@ -323,9 +341,11 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     pr.mfa.epi.colsum = p->cs_mfa;
     pr.mfa.epi.colsq = p->cq_mfa;
   }
+  SD_TRY(enable_tma_out(p, pr.mfa));
   SD_TRY(setup_tdnn_gemm(pr.att, p->h, R, C3, C3, p->watt, ATT, C3, 128, C3, 1, 1, 0, pr, p->attn,
                          ATT, 0, 0));
   pr.att.epi.utt_bias = p->uttbias;
+  pr.att.m_reverse = p->use_l2_order ? 1 : 0;  // MFA wrote h in ascending row order
   // context bias: uttbias[b, :] = W_{mean|std} . stats[b]   (per-utterance dense layer, M = B rows)
   {
     GemmParams& P = pr.ctx;
@@ -450,11 +470,17 @@ void mark(SdEcapaPlan* p, cudaStream_t st) {
 
 int launch_res2net_fused(const Res2Params& Q, cudaStream_t st) {
   static bool attr_done[64] = {};
+  // SD_R2_MODE=0: x_{i+1} loaded behind each chunk's TMEM load (the first version); 2 (default): requested before
+  // the accumulator wait / one chunk ahead (res2net 0.174 -> 0.163 ms); 1: that plus direct row-per-lane stores of
+  // y_i without the staging tile (measured SLOWER: 0.192 ms — the 16-byte pieces of 32 different lines per store)
+  static const int mode = [] { const char* e = getenv("SD_R2_MODE"); return e ? atoi(e) : 2; }();
+  void (*const kern)(const Res2Params) = mode == 0 ? res2net_fused_kernel<0> : mode == 2 ? res2net_fused_kernel<2> : res2net_fused_kernel<1>;
   if (attr_needed(attr_done)) {
-    if (cudaFuncSetAttribute(res2net_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R2_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(res2net_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared) != cudaSuccess)
-      return fail(SD_ERR_CUDA, "res2net_fused_kernel attributes: %s", cudaGetErrorString(cudaGetLastError()));
+    for (auto k : {res2net_fused_kernel<0>, res2net_fused_kernel<1>, res2net_fused_kernel<2>})
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, R2_SMEM) != cudaSuccess ||
+          cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        return fail(SD_ERR_CUDA, "res2net_fused_kernel attributes: %s", cudaGetErrorString(cudaGetLastError()));
   }
   const int grid = Q.B < 2 * num_sms() ? Q.B : 2 * num_sms();
   if (grid <= 0) return SD_OK;
@@ -465,7 +491,7 @@ int launch_res2net_fused(const Res2Params& Q, cudaStream_t st) {
     if (cudaMalloc(&dev, host.size() * 8) != cudaSuccess) return SD_ERR_CUDA;
     cudaMemsetAsync(dev, 0, host.size() * 8, st);
     T.trace = dev;
-    res2net_fused_kernel<<<grid, R2_THREADS, R2_SMEM, st>>>(T);
+    kern<<<grid, R2_THREADS, R2_SMEM, st>>>(T);
     cudaStreamSynchronize(st);
     cudaMemcpy(host.data(), dev, host.size() * 8, cudaMemcpyDeviceToHost);
     cudaFree(dev);
@@ -488,7 +514,7 @@ int launch_res2net_fused(const Res2Params& Q, cudaStream_t st) {
     count_launch();
     return SD_OK;
   }
-  cudaError_t e = launch_pdl(res2net_fused_kernel, dim3(grid), dim3(R2_THREADS), R2_SMEM, st, Q);
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(R2_THREADS), R2_SMEM, st, Q);
   count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();
   static const bool sync_debug = getenv("SD_SYNC_DEBUG") != nullptr;
@@ -553,7 +579,7 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
     const long vecs = R * (C1 / 8);
     const int grid = (int)((vecs + 255) / 256 < 148L * 16 ? (vecs + 255) / 256 : 148L * 16);
     SD_CUDA_OK(launch_pdl(se_apply_kernel, dim3(grid), dim3(256), 0, st, p->w, C1, p->se_scale, in, ld_in,
-                          p->cat + (size_t)b * C1, C3, R, Tp, C1));
+                          p->cat + (size_t)b * C1, C3, R, Tp, C1, p->use_l2_order ? 1 : 0));
     SD_CUDA_OK(cudaGetLastError());
     count_launch(4);
   }
@@ -649,6 +675,8 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   if (const char* e = getenv("SD_ECAPA_CONV3")) p->use_conv3 = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_R2FUSED")) p->use_r2fused = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_COLSUM")) p->use_colsum = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_TMAOUT")) p->use_tma_out = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_L2ORDER")) p->use_l2_order = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_MC")) p->use_mc = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_2SM")) p->use_2sm = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_PDL")) p->use_pdl = atoi(e) != 0;

@@ -259,13 +259,16 @@ se_scale_kernel(const float* __restrict__ hid, const float* __restrict__ W2t,
 __global__ void __launch_bounds__(256)
 se_apply_kernel(const __half* __restrict__ w, int ld_w, const float* __restrict__ scale,
                 const __half* __restrict__ res, int ld_res, __half* __restrict__ out, int ld_out,
-                long rows, int Tp, int C) {
+                long rows, int Tp, int C, int reverse) {
   pdl_trigger();
   pdl_wait();
   const int vec_per_row = C / 8;
   const long total = rows * vec_per_row;
-  for (long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * 256) {
+  // from the last row to the first when `reverse`: tdnn2 wrote w in ascending row order, so its last ~100 MB are
+  // still in L2 when this kernel starts
+  for (long i0 = static_cast<long>(blockIdx.x) * 256 + threadIdx.x; i0 < total;
+       i0 += static_cast<long>(gridDim.x) * 256) {
+    const long i = reverse ? total - 1 - i0 : i0;
     const long r = i / vec_per_row;
     const int c = static_cast<int>(i - r * vec_per_row) * 8;
     const int b = static_cast<int>(r / Tp);

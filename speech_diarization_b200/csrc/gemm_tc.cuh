@@ -61,6 +61,8 @@ enum { EPI_F32 = 0, EPI_TDNN = 1, EPI_POOL = 2, EPI_AFF = 3, EPI_ATT = 4, EPI_CO
 __host__ __device__ constexpr bool epi_is_tdnn(int epi) { return epi == EPI_TDNN || epi == EPI_CONV3; }
 enum {
   EF_REFLECT = 2,   // store interior rows only and mirror them into the halo rows
+  EF_TMA_OUT = 4,   // cta_group::2 kernel, pointwise layers: the staged tile leaves through TMA tensor stores
+                    // (GemmParams::tmapH = the output, tmapO2 = the out2 copy) instead of 16 LDS + 16 STG per thread
 };
 // EPI_TDNN : x = relu(acc + bias) * scale + shift                       (TDNNBlock tail)
 // EPI_ATT  : x = tanh(relu(acc + bias + utt_bias[b]) * scale + shift)   (ASP attention TDNN)
@@ -120,7 +122,9 @@ struct EpiParams {
 struct alignas(64) GemmParams {
   CUtensorMap tmapA;
   CUtensorMap tmapB;
-  CUtensorMap tmapH;  // EPI_POOL only: the h activations, box = 64 channels x n_tile rows
+  CUtensorMap tmapH;  // EPI_POOL: the h activations, box = 64 channels x n_tile rows.  EF_TMA_OUT: the output
+                      // columns [out_col_off, out_col_off + N_cols) x M_rows, box = 64 channels x 128 rows
+  CUtensorMap tmapO2; // EF_TMA_OUT with epi.out2: the first out2_cols columns of out2, same box
   int num_m_blocks, num_n_blocks, num_kiters;
   int n_tile;      // UMMA N and rows of the B box
   int a_row_base;  // added to every A row coordinate (row-block sharding)
@@ -132,6 +136,9 @@ struct alignas(64) GemmParams {
   // Measured on EPI_POOL (m fastest = all 24 channel blocks of an utterance run together): DRAM reads
   // 564 -> 531 MB but the launch got 3 % slower (0.266 -> 0.275 ms), so every caller leaves it at 0.
   int m_fastest;
+  // gemm_tc_kernel (not the EPI_CONV3 path): walk the m blocks from the last to the first.  For a consumer whose
+  // producer wrote A in ascending row order: the producer's last rows are still in L2 (126 MB) when it starts.
+  int m_reverse;
   int b_row_stride;  // 0 = n_tile (dense tiling)
   // EPI_CONV3: taps, dilation (rows), padded input channels per tap in B's K axis; kit[kc].a_col = A column
   // of 64-channel chunk kc, num_kiters = number of chunks.  tmapA's box has 128 + (taps-1)*dil rows.
@@ -369,6 +376,7 @@ __device__ __forceinline__ void tdnn_writeout(const GemmParams& P, int m_blk, in
 // 64-column chunk we>>1 and rows (we&1)*64 .. +63: a store instruction still covers four complete 128-byte
 // lines, and a column's partial sum lives in one warp (shuffle over its 4 row lanes).  The two warps of a
 // chunk combine through `part` (shared memory) in a fixed order, so the result is deterministic.
+template <bool STORE = true>   // STORE = false: statistics only, the tile itself leaves through TMA (EF_TMA_OUT)
 __device__ __forceinline__ void tdnn_writeout_colsum(const GemmParams& P, int m_blk, int n_blk,
                                                      const uint8_t* stage_out, float* part, int et) {
   const EpiParams& E = P.epi;
@@ -396,7 +404,7 @@ __device__ __forceinline__ void tdnn_writeout_colsum(const GemmParams& P, int m_
     const int r = row0 + rl;
     if (r >= E.M_rows) continue;
     const uint4 val = *reinterpret_cast<const uint4*>(sbase + rl * 128 + ((sub ^ (rl & 7)) << 4));
-    *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * E.ld_out + E.out_col_off + col) = val;
+    if (STORE) *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * E.ld_out + E.out_col_off + col) = val;
     const bool second = rl >= rb;
     const int t = second ? rl - rb - E.H : rl + tbase0;
     if (t < 0 || t >= E.T) continue;
@@ -893,8 +901,9 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
       } else
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
         const int ot = tile / k_splits, ks = tile - ot * k_splits;
-        const int m_unit = P.m_fastest ? ot % m_units : ot / P.num_n_blocks;
-        const int n_blk = P.m_fastest ? ot / m_units : ot - m_unit * P.num_n_blocks;
+        const int m_unit0 = P.m_fastest ? ot % m_units : ot / P.num_n_blocks;
+        const int n_blk = P.m_fastest ? ot / m_units : ot - m_unit0 * P.num_n_blocks;
+        const int m_unit = P.m_reverse ? m_units - 1 - m_unit0 : m_unit0;
         const int m_blk = MC ? 2 * m_unit + crank : m_unit;
         const int k_begin = ks * k_per, k_end = min(P.num_kiters, k_begin + k_per);
         for (int sub = 0; sub < n_sub; ++sub) {
@@ -996,8 +1005,9 @@ __device__ __forceinline__ void gemm_run(const GemmParams& P, const GemmCtx& c, 
     for (int tile = tile0; tile < num_tiles; tile += tstep)
     for (int sub = 0; sub < n_sub; ++sub) {
       const int ot = tile / k_splits, ksplit = tile - ot * k_splits;
-      const int m_unit = P.m_fastest ? ot % m_units : ot / P.num_n_blocks;
-      const int n_blk = P.m_fastest ? ot / m_units : ot - m_unit * P.num_n_blocks;
+      const int m_unit0 = P.m_fastest ? ot % m_units : ot / P.num_n_blocks;
+      const int n_blk = P.m_fastest ? ot / m_units : ot - m_unit0 * P.num_n_blocks;
+      const int m_unit = P.m_reverse ? m_units - 1 - m_unit0 : m_unit0;
       const int m_blk = MC ? 2 * m_unit + crank : m_unit;
       if ((epi_is_tdnn(EPI) || EPI == EPI_ATT) && n_blk != last_n_blk) {
         // stage this n block's per-column constants (the previous tile's readers all passed the
@@ -1200,6 +1210,11 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;
+    const bool tma_out = (P.epi.flags & EF_TMA_OUT) != 0;
+    if (tma_out && et == 0) {
+      tma_prefetch_desc(&P.tmapH);
+      if (P.epi.out2 != nullptr) tma_prefetch_desc(&P.tmapO2);
+    }
     int last_n_blk = -1, as = 0;
     uint32_t aphase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tstep) {
@@ -1222,16 +1237,35 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t acc = tmem_base + as * 256;
+      if (tma_out && et == 0) tma_store_wait_read();  // the previous tile's tensor stores have read the staging
       epi_named_barrier();  // every thread has finished writing out the previous tile's staging
       epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre, stage_out);
       tc_fence_before();
+      if (tma_out) fence_proxy_async();  // this thread's staging writes -> visible to the TMA engine
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);  // this CTA's share of the accumulator is drained
       if (++as == 2) { as = 0; aphase ^= 1; }
       epi_named_barrier();  // staging tile complete
-      if (P.epi.colsum != nullptr) tdnn_writeout_colsum(P, m_blk, n_blk, stage_out, epi_sp + 768, et);
-      else tdnn_writeout(P, m_blk, n_blk, stage_out, et);
+      if (tma_out) {
+        if (et == 0) {
+          // four [128 rows x 64 channels] boxes, already in the 128-byte-swizzled layout; rows >= M_rows are clipped
+          const int col0 = n_blk * 256, row0 = m_blk * BM;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            tma_store_2d(&P.tmapH, stage_out + j * 16384, col0 + j * 64, row0);
+            if (P.epi.out2 != nullptr && col0 + j * 64 < P.epi.out2_cols)
+              tma_store_2d(&P.tmapO2, stage_out + j * 16384, col0 + j * 64, row0);
+          }
+          tma_store_commit();
+        }
+        if (P.epi.colsum != nullptr) tdnn_writeout_colsum<false>(P, m_blk, n_blk, stage_out, epi_sp + 768, et);
+      } else if (P.epi.colsum != nullptr) {
+        tdnn_writeout_colsum(P, m_blk, n_blk, stage_out, epi_sp + 768, et);
+      } else {
+        tdnn_writeout(P, m_blk, n_blk, stage_out, et);
+      }
     }
+    if (tma_out && et == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
