@@ -43,7 +43,7 @@ constexpr int SUB = 128;   // Res2Net sub-band width (C1 / scale 8)
 constexpr int EMB = 192;
 constexpr int FEAT_P = 128; // 80 mel channels padded to two 64-element K chunks
 constexpr int HALO = 4;
-constexpr int KSPLIT = 8;   // split-K factor of the two per-utterance dense layers (context bias, FC)
+constexpr int KSPLIT_MAX = 32;  // split-K factor of the two per-utterance dense layers (context bias, FC): SdEcapaPlan::ksplit
 
 struct TdnnW {       // one TDNNBlock: conv weight (f16, [Cout, taps*CinP]) + folded epilogue constants
   __half* W = nullptr;
@@ -69,6 +69,16 @@ struct Program {     // launch parameters for one (B, T) shape
   cudaGraphExec_t graph = nullptr;  // captured trunk (block0 .. FC) for this shape
   int graph_launches = 0;
   int runs = 0;
+  // sd_ecapa_embed_host pipeline: block0 -> b1.tdnn1 -> b1.res2net -> b1.tdnn2 (everything before the first
+  // whole-window reduction, the SE squeeze) per upload chunk of B / NFRONT windows, so the front of chunk c runs
+  // while chunk c+1 is still crossing PCIe; the rest of the trunk ("tail") follows once for the whole batch.
+  static constexpr int NFRONT = 4;
+  bool front_built = false, front_ok = false;
+  GemmParams f_block0[NFRONT], f_tdnn1[NFRONT], f_tdnn2[NFRONT];
+  Res2Params f_r2[NFRONT];
+  cudaGraphExec_t graph_tail = nullptr;  // captured tail (b1.se .. FC)
+  int graph_tail_launches = 0;
+  int runs_tail = 0;
 };
 
 }  // namespace
@@ -112,6 +122,7 @@ struct SdEcapaPlan {
                             // launch is bound by operand ingest next to the store traffic, not by the epilogue threads' time
   bool use_l2_order = true; // SD_ECAPA_L2ORDER=0: se_apply and the attention GEMM walk the rows in ascending order like
                             // their producers (tdnn2, MFA) instead of starting with the rows those left in L2
+  int ksplit = 8;          // SD_ECAPA_KSPLIT (1..32, a divisor of 96 keeps the splits even)
   bool use_colsum = true;  // SD_ECAPA_COLSUM=0: separate passes over the activations for the SE mean and ASP mean/std
   bool use_conv3 = true;   // SD_ECAPA_CONV3=0: Res2Net convs through the generic tap-per-k-iteration path
   bool use_graph = true;   // SD_ECAPA_GRAPH=0 disables CUDA-graph replay of the trunk
@@ -121,6 +132,7 @@ struct SdEcapaPlan {
   float* h2d_buf = nullptr;
   size_t h2d_cap = 0;       // samples
   float* emb_stage = nullptr;
+  float* emb_pinned = nullptr;  // page-locked landing buffer: a device->pageable copy is staged by the driver and blocks
   int emb_cap = 0;          // windows
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[8] = {};
@@ -258,8 +270,10 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   }
   if (p->programs.size() > 256) {   // variable-length callers (embed_segments) produce many (B, T) shapes
     cudaDeviceSynchronize();  // launches that reference the cached descriptors may still be in flight
-    for (auto& kv : p->programs)
+    for (auto& kv : p->programs) {
       if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
+      if (kv.second.graph_tail) cudaGraphExecDestroy(kv.second.graph_tail);
+    }
     p->programs.clear();
     p->last = nullptr;
   }
@@ -366,7 +380,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     P.epi.N_cols = ATT;
     P.epi.out = p->ctx_part;
     P.epi.ld_out = ATT;
-    P.k_splits = KSPLIT;   // 96 k-iterations over 8 CTAs per output tile
+    P.k_splits = p->ksplit;   // 96 k-iterations over ksplit CTAs per output tile
     P.split_stride = (long)B * ATT;
   }
   // final FC (asp_bn folded): emb[b, :] = Wfc . pooled[b] + bfc
@@ -390,7 +404,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     P.epi.ld_out = EMB;
     P.epi.bias = p->bfc;
     P.epi.out = p->emb_tmp;   // [KSPLIT][B][EMB] partial sums, reduced by fc_finish_kernel
-    P.k_splits = KSPLIT;
+    P.k_splits = p->ksplit;
     P.split_stride = (long)B * EMB;
   }
   // pooling GEMM: rows = channels of asp.conv, columns = the Tp rows of one utterance
@@ -447,6 +461,46 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   }
   auto ins = p->programs.emplace(key, pr);
   *out = &ins.first->second;
+  return SD_OK;
+}
+
+// The same GEMM over the row range [row0, row0 + nrows) of its activation tensors (row0 a multiple of 128 and of
+// Tp): A is addressed through a_row_base, the outputs through offset pointers, the per-(m block, slot) column
+// sums keep their global numbering because the chunk starts on both an m-block and a window boundary.
+GemmParams sub_rows(const GemmParams& G, long row0, long nrows) {
+  GemmParams S = G;
+  S.a_row_base = G.a_row_base + static_cast<int>(row0);
+  S.num_m_blocks = static_cast<int>((nrows + BM - 1) / BM);
+  EpiParams& E = S.epi;
+  E.M_rows = static_cast<int>(nrows);
+  E.out = static_cast<__half*>(E.out) + row0 * E.ld_out;
+  if (E.out2) E.out2 += row0 * E.ld_out2;
+  if (E.colsum) E.colsum += (row0 / BM) * 2 * E.N_cols;
+  if (E.colsq) E.colsq += (row0 / BM) * 2 * E.N_cols;
+  E.flags &= ~EF_TMA_OUT;   // the output tensor maps describe the whole tensor
+  return S;
+}
+
+int build_front(SdEcapaPlan* p, Program& pr) {
+  pr.front_built = true;
+  constexpr int NF = Program::NFRONT;
+  const int nb = pr.B / NF;
+  const long nrows = static_cast<long>(nb) * pr.Tp;
+  pr.front_ok = p->use_2sm && !p->use_chain && p->use_r2fused && pr.r2_ok && pr.colsum_ok && pr.B % NF == 0 &&
+                nb >= 16 && nrows % BM == 0;
+  if (!pr.front_ok) return SD_OK;
+  for (int c = 0; c < NF; ++c) {
+    const long row0 = c * nrows;
+    pr.f_block0[c] = sub_rows(pr.block0, row0, nrows);
+    pr.f_tdnn1[c] = sub_rows(pr.tdnn1[0], row0, nrows);
+    pr.f_tdnn2[c] = sub_rows(pr.tdnn2[0], row0, nrows);
+    Res2Params& Q = pr.f_r2[c];
+    Q = pr.r2[0];
+    Q.B = nb;
+    Q.u = pr.r2[0].u + row0 * C1;
+    Q.v = pr.r2[0].v + row0 * C1;
+    SD_TRY(make_tmap_f16(&Q.tmapU, Q.u, nrows, C1, C1, pr.T + 2 * Q.dil));
+  }
   return SD_OK;
 }
 
@@ -537,17 +591,29 @@ struct PdlScope {   // programmatic dependent launch for every kernel launched i
   ~PdlScope() { pdl_flag() = false; }
 };
 
-int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
+int front_body(SdEcapaPlan* p, Program& pr, int c, cudaStream_t st) {
+  SD_TRY(launch_big(p, pr.f_block0[c], st));
+  SD_TRY(launch_big(p, pr.f_tdnn1[c], st));
+  SD_TRY(launch_res2net_fused(pr.f_r2[c], st));
+  SD_TRY(launch_big(p, pr.f_tdnn2[c], st));
+  return SD_OK;
+}
+
+// skip_front: block0 and block 1's tdnn1 / Res2Net / tdnn2 already ran per upload chunk (front_body)
+int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st, bool skip_front = false) {
   PdlScope pdl(p->use_pdl && !p->use_chain);
   const int B = pr.B, T = pr.T, Tp = pr.Tp;
   const long R = pr.rows;
   mark(p, st);  // end of fbank / start of block0
-  SD_TRY(launch_big(p, pr.block0, st));
+  if (!skip_front) SD_TRY(launch_big(p, pr.block0, st));
   for (int b = 0; b < 3; ++b) {
     const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
     const int ld_in = b == 0 ? C1 : C3;
     mark(p, st);
-    if (p->use_chain) {
+    if (skip_front && b == 0) {
+      mark(p, st);
+      mark(p, st);
+    } else if (p->use_chain) {
       // tdnn1 -> 7 dependent Res2Net convs -> tdnn2 in ONE cooperative launch (grid barrier between steps)
       SD_TRY((launch_gemm_chain<EPI_TDNN, 256>(pr.chain_dev + 9 * b, 9, st)));
       mark(p, st);
@@ -596,7 +662,7 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
   count_launch(1);
   // context bias: W_mean . mean + W_std . std  (the 2/3 of asp.tdnn that is constant over time)
   SD_TRY(launch_gemm<EPI_F32>(pr.ctx, st));
-  SD_CUDA_OK(launch_pdl(sum_splits_kernel, dim3((B * ATT + 255) / 256), dim3(256), 0, st, p->ctx_part, KSPLIT, (long)B * ATT,
+  SD_CUDA_OK(launch_pdl(sum_splits_kernel, dim3((B * ATT + 255) / 256), dim3(256), 0, st, p->ctx_part, p->ksplit, (long)B * ATT,
                         (long)B * ATT, p->uttbias));
   SD_CUDA_OK(cudaGetLastError());
   count_launch(1);
@@ -614,35 +680,38 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st) {
 // graph is static); the caller-dependent ends — fbank reading the caller's audio before it, the
 // L2-norm / copy into the caller's buffer after it — stay ordinary launches.  Replay removes
 // ~0.2 ms of launch gaps per 512-window batch (4.28 -> 4.09 ms measured).
-int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStream_t st) {
+int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStream_t st, bool skip_front = false) {
   const int B = pr.B;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   SD_CUDA_OK(cudaStreamIsCapturing(st, &cap));
   const bool can_graph = p->use_graph && !p->profile && cap == cudaStreamCaptureStatusNone;
-  if (can_graph && pr.graph) {
-    SD_CUDA_OK(cudaGraphLaunch(pr.graph, st));
-    count_launch(pr.graph_launches);
-  } else if (can_graph && pr.runs >= 2) {   // capture on the third use: one-off shapes are not worth ~1 ms
+  cudaGraphExec_t& graph = skip_front ? pr.graph_tail : pr.graph;
+  int& graph_launches = skip_front ? pr.graph_tail_launches : pr.graph_launches;
+  int& runs = skip_front ? pr.runs_tail : pr.runs;
+  if (can_graph && graph) {
+    SD_CUDA_OK(cudaGraphLaunch(graph, st));
+    count_launch(graph_launches);
+  } else if (can_graph && runs >= 2) {   // capture on the third use: one-off shapes are not worth ~1 ms
     const long before = launch_counter().load();
     cudaGraph_t g = nullptr;
     // capture on a plan-owned stream (the caller's may be the legacy default stream, which cannot
     // be captured); the instantiated graph is then launched into the caller's stream
     if (!p->cap_stream) SD_CUDA_OK(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
     SD_CUDA_OK(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = trunk_body(p, pr, p->cap_stream);
+    const int rc = trunk_body(p, pr, p->cap_stream, skip_front);
     const cudaError_t ec = cudaStreamEndCapture(p->cap_stream, &g);
     if (rc != SD_OK) { if (g) cudaGraphDestroy(g); return rc; }
     if (ec != cudaSuccess) return fail(SD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ec));
-    const cudaError_t ei = cudaGraphInstantiate(&pr.graph, g, 0);
+    const cudaError_t ei = cudaGraphInstantiate(&graph, g, 0);
     cudaGraphDestroy(g);
-    if (ei != cudaSuccess) { pr.graph = nullptr; return fail(SD_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ei)); }
-    pr.graph_launches = (int)(launch_counter().load() - before);
-    SD_CUDA_OK(cudaGraphLaunch(pr.graph, st));
+    if (ei != cudaSuccess) { graph = nullptr; return fail(SD_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ei)); }
+    graph_launches = (int)(launch_counter().load() - before);
+    SD_CUDA_OK(cudaGraphLaunch(graph, st));
   } else {
-    SD_TRY(trunk_body(p, pr, st));
+    SD_TRY(trunk_body(p, pr, st, skip_front));
   }
-  ++pr.runs;
-  fc_finish_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->emb_tmp, KSPLIT, (long)B * EMB, B, EMB, l2_normalize, 1e-8f, emb);
+  ++runs;
+  fc_finish_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->emb_tmp, p->ksplit, (long)B * EMB, B, EMB, l2_normalize, 1e-8f, emb);
   SD_CUDA_OK(cudaGetLastError());
   count_launch(1);
   mark(p, st);  // end of fc
@@ -676,6 +745,7 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   if (const char* e = getenv("SD_ECAPA_R2FUSED")) p->use_r2fused = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_COLSUM")) p->use_colsum = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_TMAOUT")) p->use_tma_out = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_KSPLIT")) p->ksplit = atoi(e) < 1 ? 1 : atoi(e) > KSPLIT_MAX ? KSPLIT_MAX : atoi(e);
   if (const char* e = getenv("SD_ECAPA_L2ORDER")) p->use_l2_order = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_MC")) p->use_mc = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_2SM")) p->use_2sm = atoi(e) != 0;
@@ -779,8 +849,8 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
     SD_TRY(dev_alloc(p, (void**)&p->stats, MB * 2 * C3 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->uttbias, MB * ATT * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->pooled, MB * 2 * C3 * 4, true));
-    SD_TRY(dev_alloc(p, (void**)&p->emb_tmp, MB * EMB * 4 * KSPLIT, true));
-    SD_TRY(dev_alloc(p, (void**)&p->ctx_part, MB * ATT * 4 * KSPLIT, true));
+    SD_TRY(dev_alloc(p, (void**)&p->emb_tmp, MB * EMB * 4 * KSPLIT_MAX, true));
+    SD_TRY(dev_alloc(p, (void**)&p->ctx_part, MB * ATT * 4 * KSPLIT_MAX, true));
     SD_TRY(dev_alloc(p, (void**)&p->stats_h, MB * 2 * C3 * 2, true));
     SD_TRY(dev_alloc(p, (void**)&p->pooled_h, MB * 2 * C3 * 2, true));
     SD_CUDA_OK(cudaDeviceSynchronize());
@@ -807,8 +877,11 @@ extern "C" int sd_ecapa_plan_destroy(SdEcapaPlan* p) {
   if (p->start_ev) cudaEventDestroy(p->start_ev);
   if (p->h2d_buf) cudaFree(p->h2d_buf);
   if (p->emb_stage) cudaFree(p->emb_stage);
-  for (auto& kv : p->programs)
+  if (p->emb_pinned) cudaFreeHost(p->emb_pinned);
+  for (auto& kv : p->programs) {
     if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
+    if (kv.second.graph_tail) cudaGraphExecDestroy(kv.second.graph_tail);
+  }
   for (void* d : p->allocs) cudaFree(d);
   delete p;
   return SD_OK;
@@ -848,9 +921,14 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
   if (B > p->emb_cap) {
     SD_CUDA_OK(cudaStreamSynchronize(st));
     if (p->emb_stage) cudaFree(p->emb_stage);
-    p->emb_stage = nullptr;
+    if (p->emb_pinned) cudaFreeHost(p->emb_pinned);
+    p->emb_stage = p->emb_pinned = nullptr;
     p->emb_cap = 0;
     SD_CUDA_OK(cudaMalloc(&p->emb_stage, static_cast<size_t>(B) * EMB * sizeof(float)));
+    if (cudaHostAlloc(&p->emb_pinned, static_cast<size_t>(B) * EMB * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      p->emb_pinned = nullptr;   // fall back to copying straight into the caller's buffer
+    }
     p->emb_cap = B;
   }
   const size_t span = static_cast<size_t>(B - 1) * wav_stride + n_samples;
@@ -867,12 +945,24 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
   SD_CUDA_OK(cudaStreamWaitEvent(p->copy_stream, p->start_ev, 0));
   mark(p, st);  // start of fbank
   const int chunks = B >= 64 ? NCH : 1;
+  // front of the trunk per upload chunk (Program::NFRONT): needs chunk boundaries on m-block boundaries
+  // Measured and rejected (off unless SD_ECAPA_PIPE=1): per-call wall clock at B = 512 went 4.01 -> 4.13 ms.  The
+  // upload costs only 0.18 ms of a call (3.83 ms with no copy at all), while a quarter-batch front is 0.16 ms
+  // slower in total than one launch per layer (128 windows leave the Res2Net kernel one CTA per SM, the GEMMs 4.3
+  // waves of tiles).
+  const char* const pipe_str = getenv("SD_ECAPA_PIPE");
+  const bool pipe_env = pipe_str && atoi(pipe_str) != 0;
+  static_assert(NCH == Program::NFRONT, "upload chunks = front chunks");
+  if (!pr->front_built) SD_TRY(build_front(p, *pr));
+  const bool piped = pipe_env && chunks == NCH && pr->front_ok && !p->profile;
   size_t copied = 0;  // samples of the span already queued (windows overlap when stride < n)
   for (int c = 0; c < chunks; ++c) {
     const int b0 = static_cast<int>(static_cast<long>(B) * c / chunks);
     const int b1 = static_cast<int>(static_cast<long>(B) * (c + 1) / chunks);
     if (b1 <= b0) continue;
-    if (wav_stride <= n_samples) {
+    static const bool nocopy = getenv("SD_DEBUG_NOCOPY") != nullptr;  // TIMING PROBE ONLY: leaves the staging as it is
+    if (nocopy) {
+    } else if (wav_stride <= n_samples) {
       const size_t end = static_cast<size_t>(b1 - 1) * wav_stride + n_samples;
       SD_CUDA_OK(cudaMemcpyAsync(p->h2d_buf + copied, wav_host + copied, (end - copied) * sizeof(float),
                                  cudaMemcpyHostToDevice, p->copy_stream));
@@ -888,10 +978,13 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
     SD_TRY(fbank_launch(p->h2d_buf + static_cast<size_t>(b0) * wav_stride, wav_stride, b1 - b0, n_samples,
                         SD_FBANK_SPEECHBRAIN, 1, p->raw + static_cast<size_t>(b0) * T * 80, nullptr,
                         p->feats + static_cast<size_t>(b0) * pr->Tp * FEAT_P, pr->Tp, HALO, st));
+    if (piped) SD_TRY(front_body(p, *pr, c, st));
   }
-  SD_TRY(run_trunk(p, *pr, l2_normalize, p->emb_stage, st));
-  SD_CUDA_OK(cudaMemcpyAsync(emb_host, p->emb_stage, static_cast<size_t>(B) * EMB * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SD_TRY(run_trunk(p, *pr, l2_normalize, p->emb_stage, st, piped));
+  const size_t emb_bytes = static_cast<size_t>(B) * EMB * sizeof(float);
+  SD_CUDA_OK(cudaMemcpyAsync(p->emb_pinned ? p->emb_pinned : emb_host, p->emb_stage, emb_bytes, cudaMemcpyDeviceToHost, st));
   SD_CUDA_OK(cudaStreamSynchronize(st));
+  if (p->emb_pinned) memcpy(emb_host, p->emb_pinned, emb_bytes);
   return SD_OK;
 }
 

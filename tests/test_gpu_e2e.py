@@ -111,19 +111,25 @@ def test_config5_dense_reassignment_pass_matches_oracle(oracle_model):
 def test_host_buffer_path_equals_device_path(oracle_model, monkeypatch):
     """ecapa_encode_batch from host memory (sd_ecapa_embed_host: chunked upload overlapped with fbank) gives
     bit-identical embeddings to the explicit upload + device path, for overlapping window views, contiguous
-    [B, n] batches, few windows (single chunk) and non-contiguous input (falls back to the torch upload)."""
+    [B, n] batches, few windows (single chunk) and non-contiguous input (falls back to the torch upload); and for
+    batches whose quarter-chunks end on 128-row boundaries, where with SD_ECAPA_PIPE=1 the front of the trunk
+    (block0 .. b1.tdnn2) runs per upload chunk (96 windows: odd m-block count per chunk, 128 windows: even)."""
     import numpy as np
     from speech_diarization_b200 import speech_encode, vad
     from conftest import synth_wave
     speech_encode.register_ecapa_state_dict(oracle_model.state_dict())
     try:
-        y = synth_wave(1, 16000 * 30, 5)[0]
-        frames = vad.frame_audio(y, 16000, 1000.0, 250.0)           # 117 overlapping windows (4 upload chunks)
+        y = synth_wave(1, 16000 * 40, 5)[0]
+        frames = vad.frame_audio(y, 16000, 1000.0, 250.0)           # 157 overlapping windows (4 upload chunks)
         dense = np.ascontiguousarray(frames[:70])                    # contiguous [70, 16000]
         few = frames[:5]                                             # one chunk
         strided = dense[::2]                                         # not contiguous, not a hop view
-        cases = {"view": frames, "dense": dense, "few": few, "strided": strided}
+        cases = {"view": frames, "dense": dense, "few": few, "strided": strided,
+                 "piped96": frames[:96], "piped128": np.ascontiguousarray(frames[:128])}
+        monkeypatch.setenv("SD_ECAPA_PIPE", "1")                     # off by default (measured slower)
         host = {k: speech_encode.ecapa_encode_batch(v) for k, v in cases.items()}
+        for _ in range(3):   # the third and later runs of a shape replay the captured tail graph
+            np.testing.assert_array_equal(speech_encode.ecapa_encode_batch(cases["piped128"]), host["piped128"])
         monkeypatch.setenv("SD_ECAPA_HOST_PATH", "0")
         dev = {k: speech_encode.ecapa_encode_batch(v) for k, v in cases.items()}
         for k in cases:
