@@ -84,8 +84,26 @@ __device__ void rescan(const ClState& S, int r, double* red_d, int* red_i) {
   const double* row = S.Dm + static_cast<size_t>(r) * S.N;
   double bd = 1e300;
   int bi = 0x7fffffff;
-  for (int k = tid; k < S.N; k += CL_THREADS)
-    if (k != r && S.active[k]) amin(bd, bi, row[k], k);
+  // eight independent (distance, liveness) loads in flight per thread: the row comes from DRAM (the matrix is
+  // 8 N^2 bytes) and a load-test-load loop of N / 256 dependent round trips made one rescan ~80 us at N = 20k —
+  // the longest pole of a step, since a step has only a handful of orphans and each is one CTA's job
+  constexpr int RU = 8;
+  for (int k0 = tid; k0 < S.N; k0 += CL_THREADS * RU) {
+    double v[RU];
+    int a[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int k = k0 + u * CL_THREADS;
+      const bool in = k < S.N;
+      v[u] = in ? row[k] : 1e300;
+      a[u] = in ? S.active[k] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int k = k0 + u * CL_THREADS;
+      if (a[u] && k != r) amin(bd, bi, v[u], k);
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double od = __shfl_xor_sync(0xffffffffu, bd, o);

@@ -15,3 +15,4 @@ python tools/ncu_target.py > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_target.csv python tools/ncu_target.py > gpurun_out/ncu_launches_target.log 2>&1
 echo "target launch list rc=$?"
 if [ "$1" == "full" ]; then bash tools/ncu_gemm.sh mfa tdnn2 r2f att pool fbank se aff ahc post; fi
+if [ "$1" == "some" ]; then shift; bash tools/ncu_gemm.sh "$@"; fi
