@@ -24,6 +24,8 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
+#include <cstdlib>
 #include "sd_ptx.cuh"
 #include "sd_status.h"
 
@@ -48,9 +50,16 @@ struct AhcState {
   int* act_list;    // [2][N] compact list of live clusters (ping-pong)
   int* counters;    // [0],[1] n_dirty ping-pong [2] n_pairs [3] rounds [4] merges [5] list length [6] list index
                     // [7] live clusters [8] staged new list length
+  long long* prof;  // debug (SD_AHC_PROF): ns per phase as seen by thread 0 of CTA 0, printed at the end
   int N;
   double thr;
 };
+
+__device__ __forceinline__ long long ahc_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // f32 [N,N] -> f64 [N,N], symmetrised from the upper triangle (sklearn reads D[i,j], i<j).
 __global__ void __launch_bounds__(256)
@@ -95,6 +104,7 @@ __global__ void ahc_init_state_kernel(AhcState S) {
     S.counters[6] = 0;
     S.counters[7] = S.N;
     S.counters[8] = 0;
+    for (int q = 16; q < 64; ++q) S.counters[q] = 0;  // phase timers (AhcState::prof)
   }
 }
 
@@ -102,6 +112,8 @@ __device__ __forceinline__ void argmin_combine(double& d, int& i, double od, int
   if (od < d || (od == d && oi < i)) { d = od; i = oi; }
 }
 
+// AHC_U = independent row entries in flight per thread (phases A, C1, C3)
+template <int AHC_U>
 __global__ void __launch_bounds__(AHC_THREADS)
 ahc_rounds_kernel(AhcState S) {
   cg::grid_group grid = cg::this_grid();
@@ -113,6 +125,14 @@ ahc_rounds_kernel(AhcState S) {
   const int gtid = blockIdx.x * AHC_THREADS + tid;
   const int gthreads = gridDim.x * AHC_THREADS;
   int cur = 0;  // which dirty counter is current
+  long long t_prev = S.prof ? ahc_now() : 0;
+  auto stamp = [&](int phase) {
+    if (S.prof != nullptr && gtid == 0) {
+      const long long t = ahc_now();
+      S.prof[phase] += t - t_prev;
+      t_prev = t;
+    }
+  };
 
   for (int round = 0; round < N; ++round) {
     // the compact list of (mostly) live clusters: late rounds touch a few hundred columns, not N
@@ -125,9 +145,24 @@ ahc_rounds_kernel(AhcState S) {
       const double* row = S.D + static_cast<size_t>(r) * N;
       double bd = 1e300;
       int bi = 0x7fffffff;
-      for (int i = tid; i < n_list; i += AHC_THREADS) {
-        const int k = list[i];
-        if (k != r && S.active[k]) argmin_combine(bd, bi, row[k], k);
+      // AHC_U independent list -> (distance, liveness) chains in flight per thread: one entry at a time is a chain
+      // of three dependent loads (list, active, the DRAM-resident row) per iteration, n_list / 256 iterations long
+      for (int i0 = tid; i0 < n_list; i0 += AHC_THREADS * AHC_U) {
+        int k[AHC_U], a[AHC_U];
+        double v[AHC_U];
+#pragma unroll
+        for (int u = 0; u < AHC_U; ++u) {
+          const int i = i0 + u * AHC_THREADS;
+          k[u] = i < n_list ? list[i] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < AHC_U; ++u) {
+          v[u] = k[u] >= 0 ? row[k[u]] : 1e300;
+          a[u] = k[u] >= 0 ? S.active[k[u]] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < AHC_U; ++u)
+          if (a[u] && k[u] != r) argmin_combine(bd, bi, v[u], k[u]);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -145,6 +180,7 @@ ahc_rounds_kernel(AhcState S) {
       __syncthreads();
     }
     grid.sync();
+    stamp(0);
 
     // ---- B: reciprocal nearest neighbours below the threshold
     for (int i = gtid; i < n_list; i += gthreads) {
@@ -160,6 +196,7 @@ ahc_rounds_kernel(AhcState S) {
       }
     }
     grid.sync();
+    stamp(1);
     const int n_pairs = S.counters[2];
     if (n_pairs == 0) break;
 
@@ -169,12 +206,24 @@ ahc_rounds_kernel(AhcState S) {
       const double ni = S.size[i], nj = S.size[j], inv = ni + nj;
       double* ri = S.D + static_cast<size_t>(i) * N;
       const double* rj = S.D + static_cast<size_t>(j) * N;
-      for (int q = tid; q < n_list; q += AHC_THREADS) {
-        const int k = list[q];
-        ri[k] = (ni * ri[k] + nj * rj[k]) / inv;
+      for (int q0 = tid; q0 < n_list; q0 += AHC_THREADS * AHC_U) {
+        int k[AHC_U];
+        double a[AHC_U], b[AHC_U];
+#pragma unroll
+        for (int u = 0; u < AHC_U; ++u) {
+          const int q = q0 + u * AHC_THREADS;
+          k[u] = q < n_list ? list[q] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < AHC_U; ++u)
+          if (k[u] >= 0) { a[u] = ri[k[u]]; b[u] = rj[k[u]]; }
+#pragma unroll
+        for (int u = 0; u < AHC_U; ++u)
+          if (k[u] >= 0) ri[k[u]] = (ni * a[u] + nj * b[u]) / inv;
       }
     }
     grid.sync();
+    stamp(2);
     // ---- C2: corners between two merged clusters (upper triangle only, i_p < i_q)
     for (long e = gtid; e < static_cast<long>(n_pairs) * n_pairs; e += gthreads) {
       const int p = static_cast<int>(e / n_pairs), q = static_cast<int>(e % n_pairs);
@@ -186,17 +235,31 @@ ahc_rounds_kernel(AhcState S) {
       }
     }
     grid.sync();
+    stamp(3);
     // ---- C3: mirror row i_p into column i_p (and the lower corners from the upper ones)
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const int i = S.pair_i[p];
       double* ri = S.D + static_cast<size_t>(i) * N;
-      for (int q = tid; q < n_list; q += AHC_THREADS) {
-        const int k = list[q];
-        if (k == i || !S.active[k]) continue;
-        const int rk = S.role[k];
-        if (rk >= 0 && (rk & 1)) continue;  // absorbed this round
-        if (rk >= 0 && k < i) ri[k] = S.D[static_cast<size_t>(k) * N + i];
-        else S.D[static_cast<size_t>(k) * N + i] = ri[k];
+      for (int q0 = tid; q0 < n_list; q0 += AHC_THREADS * AHC_U) {
+        int k[AHC_U], rk[AHC_U], act[AHC_U];
+        double v[AHC_U];
+#pragma unroll
+        for (int u = 0; u < AHC_U; ++u) {
+          const int q = q0 + u * AHC_THREADS;
+          k[u] = q < n_list ? list[q] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < AHC_U; ++u) {
+          act[u] = 0;
+          if (k[u] >= 0 && k[u] != i) { act[u] = S.active[k[u]]; rk[u] = S.role[k[u]]; v[u] = ri[k[u]]; }
+        }
+#pragma unroll
+        for (int u = 0; u < AHC_U; ++u) {
+          if (!act[u]) continue;
+          if (rk[u] >= 0 && (rk[u] & 1)) continue;  // absorbed this round
+          if (rk[u] >= 0 && k[u] < i) ri[k[u]] = S.D[static_cast<size_t>(k[u]) * N + i];
+          else S.D[static_cast<size_t>(k[u]) * N + i] = v[u];
+        }
       }
     }
     // ---- D (same phase: touches size/parent/dirty only): retire absorbed clusters, mark dirty rows
@@ -248,6 +311,7 @@ ahc_rounds_kernel(AhcState S) {
       if (tid == AHC_THREADS - 1) S.counters[8] = scan_s[tid];  // new length, committed in the clean-up phase
     }
     grid.sync();
+    stamp(4);
     // ---- clean-up
     for (int p = gtid; p < n_pairs; p += gthreads) {
       const int i = S.pair_i[p], j = S.pair_j[p];
@@ -265,7 +329,21 @@ ahc_rounds_kernel(AhcState S) {
     }
     cur = nxt;
     grid.sync();
+    stamp(5);
+    if (S.prof != nullptr && gtid == 0 && (round == 9 || round == 29 || round == 99)) {
+      const int c = round == 9 ? 0 : round == 29 ? 1 : 2;   // cumulative snapshots: where the time goes over the rounds
+      for (int q = 0; q < 6; ++q) S.prof[6 + c * 6 + q] = S.prof[q];
+    }
   }
+  if (S.prof != nullptr && gtid == 0) {
+    for (int c = 0; c < 3; ++c)
+      printf("  after %3d rounds: A %.0f  B %.0f  C1 %.0f  C2 %.0f  C3+D %.0f  cleanup %.0f\n", c == 0 ? 10 : c == 1 ? 30 : 100,
+             S.prof[6 + c * 6] * 1e-3, S.prof[7 + c * 6] * 1e-3, S.prof[8 + c * 6] * 1e-3, S.prof[9 + c * 6] * 1e-3,
+             S.prof[10 + c * 6] * 1e-3, S.prof[11 + c * 6] * 1e-3);
+  }
+  if (S.prof != nullptr && gtid == 0)
+    printf("ahc phases us: A %.0f  B %.0f  C1 %.0f  C2 %.0f  C3+D %.0f  cleanup %.0f  (grid %d CTAs)\n", S.prof[0] * 1e-3,
+           S.prof[1] * 1e-3, S.prof[2] * 1e-3, S.prof[3] * 1e-3, S.prof[4] * 1e-3, S.prof[5] * 1e-3, gridDim.x);
 }
 
 // labels[x] = rank of root(x) among the roots in ascending order (root = smallest member).
@@ -344,6 +422,7 @@ extern "C" int sd_ahc_average_f32(const float* dist_dev, int N, double threshold
   int* scratch = ip + 7 * static_cast<size_t>(N);
   S.counters = ip + 8 * static_cast<size_t>(N);
   S.act_list = ip + 8 * static_cast<size_t>(N) + 64;
+  S.prof = getenv("SD_AHC_PROF") ? reinterpret_cast<long long*>(S.counters + 16) : nullptr;
 
   const int nb = (N + 31) / 32;
   ahc_init_matrix_kernel<<<dim3(nb, nb), 256, 0, st>>>(dist_dev, N, S.D);
@@ -353,11 +432,16 @@ extern "C" int sd_ahc_average_f32(const float* dist_dev, int N, double threshold
   int dev = 0, sms = 0, occ = 0;
   SD_CUDA_OK(cudaGetDevice(&dev));
   SD_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  SD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ahc_rounds_kernel, AHC_THREADS, 0));
+  // SD_AHC_U = 1 | 4 | 8 (A/B switch): row entries in flight per thread; more means more registers, fewer CTAs
+  // (64 / 80 / 128 registers -> 4 / 3 / 2 CTAs per SM).  Measured at N = 5k / 20k / 50k: U = 1 4.06 / 33.6 / 206 ms,
+  // U = 4 3.37 / 25.5 / 149 ms, U = 8 3.48 / 27.3 / 160 ms.
+  static const int unroll = [] { const char* e = getenv("SD_AHC_U"); return e ? atoi(e) : 4; }();
+  void (*kern)(AhcState) = unroll <= 1 ? ahc_rounds_kernel<1> : unroll <= 4 ? ahc_rounds_kernel<4> : ahc_rounds_kernel<8>;
+  SD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, AHC_THREADS, 0));
   if (occ < 1) return fail(SD_ERR_CUDA, "ahc_rounds_kernel cannot be made resident");
   if (occ > 4) occ = 4;
   void* args[] = {&S};
-  SD_CUDA_OK(cudaLaunchCooperativeKernel((void*)ahc_rounds_kernel, dim3(sms * occ), dim3(AHC_THREADS), args, 0, st));
+  SD_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(sms * occ), dim3(AHC_THREADS), args, 0, st));
   ahc_labels_kernel<<<1, 1024, 0, st>>>(S, labels_dev, n_clusters_dev, scratch);
   SD_CUDA_OK(cudaGetLastError());
   count_launch(4);
