@@ -18,7 +18,8 @@
 //      whose cached nearest neighbour was merged (reducibility keeps every other cache valid).
 // It stops when no RNN pair is below the threshold, which — average linkage being monotone —
 // is the flat clustering sklearn cuts at `distance_threshold`.  The whole loop is ONE
-// persistent cooperative kernel (grid-wide barriers between phases, no host round trips).
+// persistent cooperative kernel (grid-wide barriers between phases — four per round: A | B | C1+C2 | C3+D — and no
+// host round trips).
 // Arithmetic is f64 on the f32-rounded input, as in scipy.  The matrix is HBM-resident
 // (8 N^2 bytes: 3.2 GB at N = 20k, 20 GB at 50k).
 #include <cooperative_groups.h>
@@ -134,12 +135,22 @@ ahc_rounds_kernel(AhcState S) {
     }
   };
 
+  // every thread tracks these identically (all decisions below are grid-uniform), so no phase is needed to publish them
+  int list_idx = 0, n_list = N, alive = N, prev_pairs = 0;
+  bool rebuilt = false;
+
   for (int round = 0; round < N; ++round) {
     // the compact list of (mostly) live clusters: late rounds touch a few hundred columns, not N
-    const int* list = S.act_list + static_cast<size_t>(S.counters[6]) * N;
-    const int n_list = S.counters[5];
+    if (rebuilt) { list_idx ^= 1; n_list = S.counters[8]; }   // block 0 staged the new list in the previous round
+    const int* list = S.act_list + static_cast<size_t>(list_idx) * N;
     // ---- A: nearest neighbour of every dirty row (one CTA per row)
     const int n_dirty = S.counters[cur];
+    // roles of the previous round's pairs: their last readers (C3 / D) are behind the barrier that ended that round,
+    // the next writer (B) and readers (C3 / D) are behind the barrier that ends this phase
+    for (int p = gtid; p < prev_pairs; p += gthreads) {
+      S.role[S.pair_i[p]] = -1;
+      S.role[S.pair_j[p]] = -1;
+    }
     for (int q = blockIdx.x; q < n_dirty; q += gridDim.x) {
       const int r = S.dirty_list[q];
       const double* row = S.D + static_cast<size_t>(r) * N;
@@ -183,6 +194,7 @@ ahc_rounds_kernel(AhcState S) {
     stamp(0);
 
     // ---- B: reciprocal nearest neighbours below the threshold
+    if (gtid == 0) S.counters[cur] = 0;  // every thread has read n_dirty; this counter collects the round after next's
     for (int i = gtid; i < n_list; i += gthreads) {
       const int r = list[i];
       if (!S.active[r]) continue;
@@ -221,21 +233,19 @@ ahc_rounds_kernel(AhcState S) {
         for (int u = 0; u < AHC_U; ++u)
           if (k[u] >= 0) ri[k[u]] = (ni * a[u] + nj * b[u]) / inv;
       }
-    }
-    grid.sync();
-    stamp(2);
-    // ---- C2: corners between two merged clusters (upper triangle only, i_p < i_q)
-    for (long e = gtid; e < static_cast<long>(n_pairs) * n_pairs; e += gthreads) {
-      const int p = static_cast<int>(e / n_pairs), q = static_cast<int>(e % n_pairs);
-      const int ip = S.pair_i[p], iq = S.pair_i[q], jq = S.pair_j[q];
-      if (ip < iq) {
-        const double ni = S.size[iq], nj = S.size[jq];
-        double* row = S.D + static_cast<size_t>(ip) * N;
-        row[iq] = (ni * row[iq] + nj * row[jq]) / (ni + nj);
+      // ---- C2: corners between two merged clusters (upper triangle only, i_p < i_q).  They combine two entries of
+      // THIS row, both just written by this CTA, so a CTA barrier is enough (this used to be a phase of its own)
+      __syncthreads();
+      for (int q = tid; q < n_pairs; q += AHC_THREADS) {
+        const int iq = S.pair_i[q], jq = S.pair_j[q];
+        if (i < iq) {
+          const double nq = S.size[iq], mq = S.size[jq];
+          ri[iq] = (nq * ri[iq] + mq * ri[jq]) / (nq + mq);
+        }
       }
     }
     grid.sync();
-    stamp(3);
+    stamp(2);
     // ---- C3: mirror row i_p into column i_p (and the lower corners from the upper ones)
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const int i = S.pair_i[p];
@@ -274,6 +284,7 @@ ahc_rounds_kernel(AhcState S) {
         const int j = S.pair_j[rr >> 1];
         S.size[r] += S.size[j];
         S.parent[j] = r;
+        S.active[j] = 0;   // benign for this phase's other readers: they skip j through its role as well
         dirty = true;
       } else {
         const int nn = S.nn_idx[r];
@@ -282,10 +293,10 @@ ahc_rounds_kernel(AhcState S) {
       if (dirty) S.dirty_list[atomicAdd(&S.counters[nxt], 1)] = r;
     }
     // ---- compaction of the live list (block 0, only when a quarter of it is dead)
-    const int n_alive_after = S.counters[7] - n_pairs;
+    const int n_alive_after = alive - n_pairs;
     const bool rebuild = (n_list - n_alive_after) * 4 > n_list;
     if (rebuild && blockIdx.x == 0) {
-      int* out = S.act_list + static_cast<size_t>(S.counters[6] ^ 1) * N;
+      int* out = S.act_list + static_cast<size_t>(list_idx ^ 1) * N;
       const int chunk = (n_list + AHC_THREADS - 1) / AHC_THREADS;
       const int lo = tid * chunk, hi = min(n_list, lo + chunk);
       int cnt = 0;
@@ -308,28 +319,20 @@ ahc_rounds_kernel(AhcState S) {
         const int rk = S.role[k];
         if (S.active[k] && !(rk >= 0 && (rk & 1))) out[w++] = k;
       }
-      if (tid == AHC_THREADS - 1) S.counters[8] = scan_s[tid];  // new length, committed in the clean-up phase
+      if (tid == AHC_THREADS - 1) S.counters[8] = scan_s[tid];  // new length, picked up by every thread at the top of the next round
     }
-    grid.sync();
-    stamp(4);
-    // ---- clean-up
-    for (int p = gtid; p < n_pairs; p += gthreads) {
-      const int i = S.pair_i[p], j = S.pair_j[p];
-      S.active[j] = 0;
-      S.role[i] = -1;
-      S.role[j] = -1;
-    }
-    if (gtid == 0) {
-      S.counters[cur] = 0;  // consumed dirty counter becomes next round's target
+    if (gtid == 0) {   // n_pairs was read by everyone two barriers ago; statistics for sd_ahc_read_stats
       S.counters[2] = 0;
       S.counters[3] = round + 1;
       S.counters[4] += n_pairs;
       S.counters[7] = n_alive_after;
-      if (rebuild) { S.counters[5] = S.counters[8]; S.counters[6] ^= 1; }
     }
+    alive = n_alive_after;
+    prev_pairs = n_pairs;
+    rebuilt = rebuild;
     cur = nxt;
     grid.sync();
-    stamp(5);
+    stamp(4);
     if (S.prof != nullptr && gtid == 0 && (round == 9 || round == 29 || round == 99)) {
       const int c = round == 9 ? 0 : round == 29 ? 1 : 2;   // cumulative snapshots: where the time goes over the rounds
       for (int q = 0; q < 6; ++q) S.prof[6 + c * 6 + q] = S.prof[q];
