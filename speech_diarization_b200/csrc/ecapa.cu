@@ -235,6 +235,7 @@ int setup_tdnn_gemm(GemmParams& P, const __half* A, long rows, int a_cols, int l
   P.num_kiters = ki;
   EpiParams& E = P.epi;
   E.flags = flags;
+  if (const char* e = getenv("SD_ECAPA_APF")) P.a_prefetch = atoi(e) < 0 ? 0 : atoi(e) > 64 ? 64 : atoi(e);
   if (const char* e = getenv("SD_DEBUG_EPI")) E.flags |= (atoi(e) == 1 ? 64 : atoi(e) == 2 ? 128 : atoi(e) == 3 ? 256 : 0);
   E.M_rows = (int)rows;
   E.N_cols = cout;

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <vector>
 #include "gemm_tc.cuh"
 #include "sd_status.h"
 
@@ -193,6 +194,30 @@ inline int launch_gemm_2sm(const GemmParams& P, cudaStream_t stream) {
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_flag() ? 2 : 1;
+  if (const char* path = getenv("SD_GEMM_TRACE")) {   // debug: clock stamps of CTA 0 for launches with num_kiters == SD_GEMM_TRACE_K
+    const char* ks = getenv("SD_GEMM_TRACE_K");
+    if (P.num_kiters == (ks ? atoi(ks) : 16)) {
+      GemmParams T = P;
+      long long* dev = nullptr;
+      std::vector<long long> host(32 * 16, 0);
+      if (cudaMalloc(&dev, host.size() * 8) != cudaSuccess) return SD_ERR_CUDA;
+      cudaMemsetAsync(dev, 0, host.size() * 8, stream);
+      T.trace = dev;
+      cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI_TDNN>, T);
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(host.data(), dev, host.size() * 8, cudaMemcpyDeviceToHost);
+      cudaFree(dev);
+      if (FILE* f = fopen(path, "w")) {
+        for (int t = 0; t < 32; ++t) {
+          for (int k = 0; k < 16; ++k) fprintf(f, "%lld ", host[t * 16 + k] ? host[t * 16 + k] - host[0] : -1LL);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+      count_launch();
+      return SD_OK;
+    }
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_2sm_kernel<EPI_TDNN>, P);
   count_launch();
   static const bool sync_debug = getenv("SD_SYNC_DEBUG") != nullptr;

@@ -150,6 +150,8 @@ struct alignas(64) GemmParams {
   int k_splits;  // >= 1
   long split_stride;
   uint32_t idesc;
+  int a_prefetch;    // cta_group::2 kernel: k-iterations of A pulled into L2 ahead of the TMA loads (0 = off)
+  long long* trace;  // debug (SD_GEMM_TRACE, cta_group::2 kernel): clock64 stamps of CTA 0, [tile < 32][16]
   KIter kit[MAX_KITERS];
   EpiParams epi;
 };
@@ -1106,7 +1108,10 @@ struct Cfg2sm {
   static constexpr int A_BYTES = BM * BK * 2;             // 16 KB: this CTA's 128 rows of A
   static constexpr int B_BYTES = 128 * BK * 2;            // 16 KB: this CTA's half of the 256-row B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
-  static constexpr int STAGES = 4;
+#ifndef SD_2SM_STAGES
+#define SD_2SM_STAGES 4
+#endif
+  static constexpr int STAGES = SD_2SM_STAGES;
   static constexpr int OUT_STAGE_BYTES = 65536;
   static constexpr int EPI_BYTES = (3 * 256 + 1024) * 4;   // per-column constants + colsum exchange
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + EPI_BYTES + 256;
@@ -1165,11 +1170,25 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // L2 prefetch of the A boxes `pf` k-iterations ahead of the loads (GemmParams::a_prefetch): the four-stage
+      // ring holds 128 KB in flight per SM, which covers ~2000 cycles of load latency at one k-iteration per 512
+      // cycles only just (SD_GEMM_TRACE: the MMA thread waits on full[] — 650 cycles per k-iteration); A streams from
+      // HBM, so the ring is effectively deepened in L2, where it costs no shared memory.  (B, the weights, is L2-resident.)
+      const int pf = P.a_prefetch;
+      int pf_tile = tile0, pf_k = 0;
+      auto prefetch_next = [&]() {
+        if (pf_tile >= num_tiles) return;
+        const int pm = pf_tile / P.num_n_blocks;
+        tma_prefetch_l2_2d(&P.tmapA, P.kit[pf_k].a_col, P.a_row_base + (2 * pm + crank) * BM + P.kit[pf_k].a_row_off);
+        if (++pf_k == P.num_kiters) { pf_k = 0; pf_tile += tstep; }
+      };
+      for (int i = 0; i < pf; ++i) prefetch_next();
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
         const int m_unit = tile / P.num_n_blocks;
         const int n_blk = tile - m_unit * P.num_n_blocks;
         const int m_blk = 2 * m_unit + crank;
         for (int k = 0; k < P.num_kiters; ++k) {
+          if (pf > 0) prefetch_next();
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -1187,8 +1206,11 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        const int tl = (tile - tile0) / tstep;   // this CTA pair's tile counter (trace slot)
+        if (P.trace && blockIdx.x == 0 && tl < 32) P.trace[tl * 16 + 0] = clock64();
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
+        if (P.trace && blockIdx.x == 0 && tl < 32) P.trace[tl * 16 + 1] = clock64();
         const uint32_t acc = tmem_base + as * 256;
         for (int k = 0; k < P.num_kiters; ++k) {
           mbar_wait(&full_bar[stage], phase);
@@ -1203,6 +1225,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_2sm(&tfull_bar[as], 0x3);       // accumulators complete in both CTAs' TMEM
+        if (P.trace && blockIdx.x == 0 && tl < 32) P.trace[tl * 16 + 2] = clock64();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -1234,18 +1257,26 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
       }
       uint4 pre[2][4];
       tdnn_prefetch(P, m_blk, n_blk, quarter, half, lane, pre);
+      const int tl = (tile - tile0) / tstep;
+      const bool tr = P.trace != nullptr && blockIdx.x == 0 && tl < 32 && lane == 0 && (warp == 2 || warp == 9);
+      long long* const tp = P.trace + tl * 16 + (warp == 2 ? 3 : 9);
+      if (tr) tp[0] = clock64();
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      if (tr) tp[1] = clock64();
       const uint32_t acc = tmem_base + as * 256;
       if (tma_out && et == 0) tma_store_wait_read();  // the previous tile's tensor stores have read the staging
       epi_named_barrier();  // every thread has finished writing out the previous tile's staging
+      if (tr) tp[2] = clock64();
       epilogue_tdnn<false>(P, m_blk, n_blk, acc, quarter, half, lane, epi_sp, pre, stage_out);
+      if (tr) tp[3] = clock64();
       tc_fence_before();
       if (tma_out) fence_proxy_async();  // this thread's staging writes -> visible to the TMA engine
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);  // this CTA's share of the accumulator is drained
       if (++as == 2) { as = 0; aphase ^= 1; }
       epi_named_barrier();  // staging tile complete
+      if (tr) tp[4] = clock64();
       if (tma_out) {
         if (et == 0) {
           // four [128 rows x 64 channels] boxes, already in the 128-byte-swizzled layout; rows >= M_rows are clipped
@@ -1264,6 +1295,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
       } else {
         tdnn_writeout(P, m_blk, n_blk, stage_out, et);
       }
+      if (tr) tp[5] = clock64();
     }
     if (tma_out && et == 0) tma_store_wait_all();
   }

@@ -122,6 +122,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap
         "r"(c0), "r"(c1)
       : "memory");
 }
+// Pull a tensor-map box towards L2 without a shared-memory destination (no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // arrive on the barrier at this offset in the leader CTA
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
