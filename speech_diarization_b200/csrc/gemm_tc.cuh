@@ -1108,6 +1108,9 @@ struct Cfg2sm {
   static constexpr int A_BYTES = BM * BK * 2;             // 16 KB: this CTA's 128 rows of A
   static constexpr int B_BYTES = 128 * BK * 2;            // 16 KB: this CTA's half of the 256-row B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
+#ifndef SD_TRACE_ON
+#define SD_TRACE_ON 1   // clock-stamp trace of the cta_group::2 kernel compiled in (GemmParams::trace, null in production)
+#endif
 #ifndef SD_2SM_STAGES
 #define SD_2SM_STAGES 4
 #endif
@@ -1187,15 +1190,22 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
         const int m_unit = tile / P.num_n_blocks;
         const int n_blk = tile - m_unit * P.num_n_blocks;
         const int m_blk = 2 * m_unit + crank;
+        // everything the two TMA instructions need is in registers BEFORE the wait for the free stage: the time
+        // from "stage free" to "loads issued" adds to the load latency the four-stage ring has to cover
+        const int a_row0 = P.a_row_base + m_blk * BM, b_row = n_blk * P.n_tile + crank * 128;
+        int a_col = P.kit[0].a_col, a_off = P.kit[0].a_row_off, b_col = P.kit[0].b_col;
         for (int k = 0; k < P.num_kiters; ++k) {
           if (pf > 0) prefetch_next();
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes
+          const int kn = k + 1 < P.num_kiters ? k + 1 : 0;
+          const int na_col = P.kit[kn].a_col, na_off = P.kit[kn].a_row_off, nb_col = P.kit[kn].b_col;
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          tma_load_2d_2sm(sa, &P.tmapA, &full_bar[stage], P.kit[k].a_col,
-                          P.a_row_base + m_blk * BM + P.kit[k].a_row_off);
-          tma_load_2d_2sm(sa + Cfg::A_BYTES, &P.tmapB, &full_bar[stage], P.kit[k].b_col,
-                          n_blk * P.n_tile + crank * 128);
+          uint64_t* const fb = &full_bar[stage];
+          const int a_row = a_row0 + a_off;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(fb, 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes
+          tma_load_2d_2sm(sa, &P.tmapA, fb, a_col, a_row);
+          tma_load_2d_2sm(sa + Cfg::A_BYTES, &P.tmapB, fb, b_col, b_row);
+          a_col = na_col; a_off = na_off; b_col = nb_col;
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -1207,10 +1217,10 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
       uint32_t phase = 0, aphase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
         const int tl = (tile - tile0) / tstep;   // this CTA pair's tile counter (trace slot)
-        if (P.trace && blockIdx.x == 0 && tl < 32) P.trace[tl * 16 + 0] = clock64();
+        if (SD_TRACE_ON && P.trace && blockIdx.x == 0 && tl < 32) P.trace[tl * 16 + 0] = clock64();
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
-        if (P.trace && blockIdx.x == 0 && tl < 32) P.trace[tl * 16 + 1] = clock64();
+        if (SD_TRACE_ON && P.trace && blockIdx.x == 0 && tl < 32) P.trace[tl * 16 + 1] = clock64();
         const uint32_t acc = tmem_base + as * 256;
         for (int k = 0; k < P.num_kiters; ++k) {
           mbar_wait(&full_bar[stage], phase);
@@ -1220,12 +1230,12 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
           const uint64_t db = make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; ++kk)
-            umma_f16_2sm(acc, da + 2 * kk, db + 2 * kk, idesc, (P.kit[k].accum | kk) ? 1u : 0u);
+            umma_f16_2sm(acc, da + 2 * kk, db + 2 * kk, idesc, (k | kk) ? 1u : 0u);  // kit[k].accum == (k > 0) for every TDNN layer
           umma_commit_2sm(&empty_bar[stage], 0x3);  // frees this stage in BOTH CTAs
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_2sm(&tfull_bar[as], 0x3);       // accumulators complete in both CTAs' TMEM
-        if (P.trace && blockIdx.x == 0 && tl < 32) P.trace[tl * 16 + 2] = clock64();
+        if (SD_TRACE_ON && P.trace && blockIdx.x == 0 && tl < 32) P.trace[tl * 16 + 2] = clock64();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -1258,7 +1268,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
       uint4 pre[2][4];
       tdnn_prefetch(P, m_blk, n_blk, quarter, half, lane, pre);
       const int tl = (tile - tile0) / tstep;
-      const bool tr = P.trace != nullptr && blockIdx.x == 0 && tl < 32 && lane == 0 && (warp == 2 || warp == 9);
+      const bool tr = SD_TRACE_ON && P.trace != nullptr && blockIdx.x == 0 && tl < 32 && lane == 0 && (warp == 2 || warp == 9);
       long long* const tp = P.trace + tl * 16 + (warp == 2 ? 3 : 9);
       if (tr) tp[0] = clock64();
       mbar_wait(&tfull_bar[as], aphase);
