@@ -355,9 +355,15 @@ __device__ __forceinline__ void tdnn_writeout(const GemmParams& P, int m_blk, in
     }
     if (!valid) continue;
     const uint8_t* srow = stage_out + rl * 128 + ((sub ^ (rl & 7)) << 4);
-    for (int j = 0; j < nchunks; ++j) {
+    uint4 vals[4];   // the row's (at most four) 16-byte pieces first, then the stores: four shared loads in flight
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nchunks) vals[j] = *reinterpret_cast<const uint4*>(srow + j * 16384);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= nchunks) break;
       const int col = n_blk * P.n_tile + j * 64 + sub * 8;
-      const uint4 val = *reinterpret_cast<const uint4*>(srow + j * 16384);
+      const uint4 val = vals[j];
       const size_t coff = static_cast<size_t>(E.out_col_off + col);
       *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * E.ld_out + coff) = val;
       if (r2 >= 0) *reinterpret_cast<uint4*>(out + static_cast<size_t>(r2) * E.ld_out + coff) = val;
