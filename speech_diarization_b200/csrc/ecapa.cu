@@ -913,10 +913,12 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
   Program* pr = nullptr;
   SD_TRY(build_program(p, B, T, &pr));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  constexpr int NCH = 4;
+  constexpr int NCH_MAX = 8;   // = sizeof(copy_ev) / sizeof(copy_ev[0])
+  // upload chunks (SD_ECAPA_UPCHUNKS = 1..8): more chunks expose less of the first one, each costs an event round trip
+  static const int NCH = [] { const char* e = getenv("SD_ECAPA_UPCHUNKS"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : v > NCH_MAX ? NCH_MAX : v; }();
   if (!p->copy_stream) {
     SD_CUDA_OK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-    for (int c = 0; c < NCH; ++c) SD_CUDA_OK(cudaEventCreateWithFlags(&p->copy_ev[c], cudaEventDisableTiming));
+    for (int c = 0; c < NCH_MAX; ++c) SD_CUDA_OK(cudaEventCreateWithFlags(&p->copy_ev[c], cudaEventDisableTiming));
     SD_CUDA_OK(cudaEventCreateWithFlags(&p->start_ev, cudaEventDisableTiming));
   }
   if (B > p->emb_cap) {
@@ -953,9 +955,8 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
   // waves of tiles).
   const char* const pipe_str = getenv("SD_ECAPA_PIPE");
   const bool pipe_env = pipe_str && atoi(pipe_str) != 0;
-  static_assert(NCH == Program::NFRONT, "upload chunks = front chunks");
   if (!pr->front_built) SD_TRY(build_front(p, *pr));
-  const bool piped = pipe_env && chunks == NCH && pr->front_ok && !p->profile;
+  const bool piped = pipe_env && chunks == Program::NFRONT && pr->front_ok && !p->profile;
   size_t copied = 0;  // samples of the span already queued (windows overlap when stride < n)
   for (int c = 0; c < chunks; ++c) {
     const int b0 = static_cast<int>(static_cast<long>(B) * c / chunks);
