@@ -199,13 +199,28 @@ __device__ __forceinline__ void epilogue_f32(const GemmParams& P, int m_blk, int
     tmem_ld_wait();
     if (r < E.M_rows) {
       const int col0 = n_blk * P.n_tile + c0;
-      float* dst = out + static_cast<size_t>(r) * E.ld_out + E.out_col_off + col0;
+      float* dst = out + static_cast<size_t>(r) * E.ld_out + E.out_col_off + col0 + ksplit * P.split_stride;
+      if (col0 + 16 <= E.N_cols && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        // the thread's 16 consecutive floats as four 16-byte stores: a warp's store instruction touches 32 rows either
+        // way, but with 16 instead of 4 useful bytes per sector (the scalar form made the skinny split-K layers —
+        // context bias, FC — spend most of their time in L2 store transactions)
+        const bool wb = E.bias != nullptr && ksplit == 0;
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (col0 + j < E.N_cols) {
-          dst[j + ksplit * P.split_stride] =
-              __uint_as_float(v[j]) + ((E.bias && ksplit == 0) ? __ldg(E.bias + col0 + j) : 0.f);
+        for (int q = 0; q < 4; ++q) {
+          float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+          if (wb) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(E.bias + col0) + q);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          }
+          reinterpret_cast<float4*>(dst)[q] = o;
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (col0 + j < E.N_cols)
+            dst[j] = __uint_as_float(v[j]) + ((E.bias && ksplit == 0) ? __ldg(E.bias + col0 + j) : 0.f);
+      }
     }
   }
 }
