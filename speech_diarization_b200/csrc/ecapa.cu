@@ -343,6 +343,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
       Q.H = HALO;
       Q.dil = bw.dil;
       Q.idesc = make_idesc_f16(SUB, 0);
+      Q.idesc_t1 = make_idesc_f16(32, 0);
     }
     SD_TRY(setup_tdnn_gemm(pr.tdnn2[b], p->v, R, C1, C1, bw.tdnn2, C1, C1, 256, C1, 1, 1, 0, pr,
                            p->w, C1, 0, 0, p->use_mc || p->use_2sm));
@@ -525,13 +526,14 @@ void mark(SdEcapaPlan* p, cudaStream_t st) {
 
 int launch_res2net_fused(const Res2Params& Q, cudaStream_t st) {
   static bool attr_done[64] = {};
-  // SD_R2_MODE=0: x_{i+1} loaded behind each chunk's TMEM load (the first version); 2 (default): requested before
-  // the accumulator wait / one chunk ahead (res2net 0.174 -> 0.163 ms); 1: that plus direct row-per-lane stores of
+  // SD_R2_MODE=0: x_{i+1} loaded behind each chunk's TMEM load (the first version, 0.174 ms per block at B = 512);
+  // 2: requested before the accumulator wait / one chunk ahead (0.163 ms); 3 (default): 2 + the frames beyond 127
+  // computed transposed, their epilogue spread over all eight warps (0.148 ms); 1: 2 + direct row-per-lane stores of
   // y_i without the staging tile (measured SLOWER: 0.192 ms — the 16-byte pieces of 32 different lines per store)
-  static const int mode = [] { const char* e = getenv("SD_R2_MODE"); return e ? atoi(e) : 2; }();
-  void (*const kern)(const Res2Params) = mode == 0 ? res2net_fused_kernel<0> : mode == 2 ? res2net_fused_kernel<2> : res2net_fused_kernel<1>;
+  static const int mode = [] { const char* e = getenv("SD_R2_MODE"); return e ? atoi(e) : 3; }();
+  void (*const kern)(const Res2Params) = mode == 0 ? res2net_fused_kernel<0> : mode == 2 ? res2net_fused_kernel<2> : mode == 3 ? res2net_fused_kernel<3> : res2net_fused_kernel<1>;
   if (attr_needed(attr_done)) {
-    for (auto k : {res2net_fused_kernel<0>, res2net_fused_kernel<1>, res2net_fused_kernel<2>})
+    for (auto k : {res2net_fused_kernel<0>, res2net_fused_kernel<1>, res2net_fused_kernel<2>, res2net_fused_kernel<3>})
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, R2_SMEM) != cudaSuccess ||
           cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
                                cudaSharedmemCarveoutMaxShared) != cudaSuccess)

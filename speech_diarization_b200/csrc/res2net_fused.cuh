@@ -59,6 +59,7 @@ struct alignas(64) Res2Params {
   int ld;
   int B, T, Tp, H, dil;
   uint32_t idesc;                 // M = 128, N = 128, f16
+  uint32_t idesc_t1;              // M = 128, N = 32, f16: MODE 3's transposed second tile
   long long* trace;               // debug (SD_R2_TRACE): CTA 0's per-conv clock64 stamps, [conv][18]
 };
 
@@ -77,6 +78,11 @@ __device__ __forceinline__ void r2_stamp(const Res2Params& P, int n, int slot) {
 //         chunk k+1 as soon as chunk k has consumed its own: 0.174 -> 0.163 ms per block at B = 512.
 // MODE 1: MODE 2 + y_i stored straight from the registers (one row per lane, 4 x 16 B) without the staging round
 //         trip.  Measured slower (0.192 ms): every store instruction then touches 32 different lines.
+// MODE 3: MODE 2 + the frames beyond 127 (23 of them at T = 151) are computed TRANSPOSED: D1^T[channel, frame] =
+//         W . X^T with M = 128 channels (TMEM lanes) and N = 32 frames (TMEM columns 128-159) instead of a second
+//         128-row M tile of which 105 rows are waste.  A quarter of the tensor work of that tile, and — the point —
+//         its epilogue is spread over all eight warps (32 channels x 16 frames each) instead of sitting on the two
+//         warps that own TMEM lanes 0-31: the serial conv-to-conv path shrinks from 4 to 2.5 chunk units.
 template <int MODE>
 __global__ void __launch_bounds__(R2_THREADS, 2)
 res2net_fused_kernel(const __grid_constant__ Res2Params P) {
@@ -167,7 +173,14 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
               tc_fence_after();
               if (P.trace != nullptr && blockIdx.x == 0 && n < 32) P.trace[1600 + n * 12 + (kc * 3 + j) * 2 + 1] = clock64();
               const uint64_t db = make_smem_desc_sw128(smem_u32(wring + slot * R2_WBOX));
-              for (int m = 0; m < n_mt; ++m) {
+              if (MODE == 3 && n_mt > 1) {
+                // frames 128.. transposed: "A" = the weight box (128 output channels), "B" = 32 rows of the input
+                const uint64_t dx = make_smem_desc_sw128(a_addr0 + kc * R2_A_CHUNK + (128 + j * d) * 128);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16(tmem_base + 128, db + 2 * kk, dx + 2 * kk, P.idesc_t1, (kc | j | kk) ? 1u : 0u);
+              }
+              for (int m = 0; m < (MODE == 3 ? 1 : n_mt); ++m) {
                 // tap j of M tile m: rows m*128 + j*d .. of the same buffer (row pitch 128 B)
                 const uint64_t da = make_smem_desc_sw128(a_addr0 + kc * R2_A_CHUNK + (m * 128 + j * d) * 128);
 #pragma unroll
@@ -200,8 +213,15 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     // number of (M tile, 32-column) chunks this warp works through per conv
-    const int my_mt = (quarter * 32 < T ? 1 : 0) + (128 + quarter * 32 < T ? 1 : 0);
+    const int my_mt = (quarter * 32 < T ? 1 : 0) + ((MODE != 3 && 128 + quarter * 32 < T) ? 1 : 0);
     const int nk = 2 * my_mt;
+    // MODE 3: this warp's share of the transposed tile: channels quarter*32 + lane, frames 128 + half*16 .. +15
+    // (the frames beyond 127 are split evenly between the two warps of a quarter: 12 + 11 at T = 151)
+    const bool has_t1 = MODE == 3 && T > 128;
+    const int t1_h0 = (T - 128 + 1) >> 1;
+    const int t1_f0 = 128 + half * t1_h0;
+    const int t1_end = half == 0 ? 128 + t1_h0 : T;
+    const int t1_c = quarter * 32 + lane;
     int n = 0;
     for (int ws = blockIdx.x; ws < P.B; ws += gridDim.x) {
       const int w = P.B - 1 - ws;
@@ -242,9 +262,53 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
           }
         };
         if (MODE != 0 && has_next && nk > 0) load_xc(0);
+        uint32_t xt[8];   // MODE 3: x_{i+1}[frame, this channel] for the 16 transposed frames, two f16 per register
+        if (has_t1 && has_next) {
+          const unsigned short* xs = reinterpret_cast<const unsigned short*>(xnext) + t1_c - half * 64;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int t = t1_f0 + 2 * jj;
+            const uint32_t lo = t < t1_end ? __ldg(xs + static_cast<size_t>(t) * ld) : 0u;
+            const uint32_t hi = t + 1 < t1_end ? __ldg(xs + static_cast<size_t>(t + 1) * ld) : 0u;
+            xt[jj] = lo | (hi << 16);
+          }
+        }
         mbar_wait(t_full, n & 1);
         tc_fence_after();
         if (lane == 0) r2_stamp(P, n, 2 + 2 * (warp - 2));
+        if (has_t1) {
+          uint32_t acc[16];
+          __syncwarp();
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t1_f0, acc);
+          tmem_ld_wait();
+          const float cb = cs[t1_c], csc = cs[128 + t1_c], csh = cs[256 + t1_c];
+          __half* const vcol = P.v + (i + 1) * R2_SUB + t1_c + (wrow + H) * ld;   // this channel's column of y_i
+          uint8_t* const acol = abuf + (t1_c >> 6) * R2_A_CHUNK + (t1_c & 7) * 2;
+          const int piece = (t1_c & 63) >> 3;
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int t = t1_f0 + jj;
+            if (t < t1_end) {
+              const __half y = __float2half_rn(fmaf(fmaxf(__uint_as_float(acc[jj]) + cb, 0.f), csc, csh));
+              vcol[static_cast<long>(t) * ld] = y;
+              if (t >= T - 1 - H && t <= T - 2) vcol[static_cast<long>(2 * (T - 1) - t) * ld] = y;
+              if (has_next) {
+                const __half xv = __ushort_as_half(static_cast<unsigned short>(jj & 1 ? xt[jj >> 1] >> 16 : xt[jj >> 1] & 0xffffu));
+                const __half sv = __hadd(xv, y);
+                const int p = t + d;
+                *reinterpret_cast<__half*>(acol + p * 128 + ((piece ^ (p & 7)) << 4)) = sv;
+                if (t >= T - 1 - d && t <= T - 2) {
+                  const int p2 = d + 2 * (T - 1) - t;
+                  *reinterpret_cast<__half*>(acol + p2 * 128 + ((piece ^ (p2 & 7)) << 4)) = sv;
+                }
+              }
+            }
+          }
+          if (nk == 0) {   // no tile-0 rows for this quarter (cannot happen with T > 128, kept for symmetry)
+            tc_fence_before();
+            if (has_next) fence_proxy_async();
+          }
+        }
         for (int k = 0; k < nk; ++k) {
           const int mt = k >> 1, ci = k & 1;
           const int tw0 = mt * 128 + quarter * 32;  // first frame of this warp's 32 rows
