@@ -183,7 +183,7 @@ struct StateDict {
 // w_cols restricts the repack to the first w_cols input channels (ASP: x part only).
 int load_tdnn(SdEcapaPlan* p, const StateDict& sd, const std::string& prefix, int cout, int cin,
               int taps, int cin_p, int w_cols, TdnnW* out) {
-  const float *W, *b, *g, *be, *rm, *rv;
+  const float *W = nullptr, *b = nullptr, *g = nullptr, *be = nullptr, *rm = nullptr, *rv = nullptr;
   SD_TRY(sd.get(prefix + ".conv.conv.weight", (int64_t)cout * cin * taps, &W));
   SD_TRY(sd.get(prefix + ".conv.conv.bias", cout, &b));
   SD_TRY(sd.get(prefix + ".norm.norm.weight", cout, &g));
@@ -541,7 +541,8 @@ int launch_res2net_fused(const Res2Params& Q, cudaStream_t st) {
   }
   const int grid = Q.B < 2 * num_sms() ? Q.B : 2 * num_sms();
   if (grid <= 0) return SD_OK;
-  if (const char* path = getenv("SD_R2_TRACE")) {   // debug: dump CTA 0's per-conv clock stamps (no graph capture)
+  static const char* const r2_trace_path = getenv("SD_R2_TRACE");   // read once: this runs per launch
+  if (const char* path = r2_trace_path) {   // debug: dump CTA 0's per-conv clock stamps (no graph capture)
     Res2Params T = Q;
     long long* dev = nullptr;
     std::vector<long long> host(32 * 18 + 32 * 4 * 8 + 32 * 12, 0);

@@ -194,8 +194,9 @@ inline int launch_gemm_2sm(const GemmParams& P, cudaStream_t stream) {
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_flag() ? 2 : 1;
-  if (const char* path = getenv("SD_GEMM_TRACE")) {   // debug: clock stamps of CTA 0 for launches with num_kiters == SD_GEMM_TRACE_K
-    const char* ks = getenv("SD_GEMM_TRACE_K");
+  static const char* const trace_path = getenv("SD_GEMM_TRACE");   // read once: this runs per launch
+  if (const char* path = trace_path) {   // debug: clock stamps of CTA 0 for launches with num_kiters == SD_GEMM_TRACE_K
+    static const char* const ks = getenv("SD_GEMM_TRACE_K");
     if (P.num_kiters == (ks ? atoi(ks) : 16)) {
       GemmParams T = P;
       long long* dev = nullptr;
