@@ -37,11 +37,12 @@ def test_trunk_layerwise_and_embedding_parity(oracle_model, encoder, B, T):
     assert _rel(got, ref) < 5e-3
 
 
-@pytest.mark.parametrize("B,T", [(300, 151), (5, 101), (3, 160), (2, 16), (9, 129), (4, 128), (2, 161)])
+@pytest.mark.parametrize("B,T", [(300, 151), (5, 101), (3, 160), (2, 16), (9, 129), (4, 128), (2, 161), (3, 131), (3, 137)])
 def test_fused_res2net_is_bit_identical_to_the_per_conv_chain(oracle_model, B, T, monkeypatch):
     """res2net_fused_kernel (one launch per block, inputs kept in shared memory) keeps the operand order and
     f16 rounding points of the per-convolution chain, so v after every block and the embeddings must be
-    bit-identical.  B = 300 > 2 x 148 CTAs exercises the multi-window loop; T = 161 falls back."""
+    bit-identical.  B = 300 > 2 x 148 CTAs exercises the multi-window loop; T = 161 falls back; T = 129 .. 160 run the
+    transposed second tile (T = 131: the mirrored right-halo frames straddle the two tiles)."""
     x = eo.synth_features(B, T, seed=7 * B + T)
     out = {}
     for fused in ("1", "0"):
