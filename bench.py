@@ -233,6 +233,95 @@ def run_reference_arm(args, rank: int) -> None:
     emit(line)
 
 
+# --------------------------------------------------------------------- GPU-library comparator
+def torch_gpu_setup(state_dict, device):
+    """The reference's own GPU arithmetic: stock PyTorch (cuDNN / cuBLAS / cuFFT) with TF32 allowed exactly as
+    diarization_baseline.py:20-21 sets it, running the oracle's restatement of speechbrain's Fbank + ECAPA-TDNN
+    (the model `speech_encode.py:64-78` would run) on the GPU.  A baseline leg: nothing of this repo's CUDA."""
+    from oracle import ecapa_oracle
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    model = ecapa_oracle.ECAPA_TDNN().eval()
+    model.load_state_dict(state_dict)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return ecapa_oracle, model.to(device)
+
+
+def torch_gpu_bench(state_dict, audio_dev: torch.Tensor, frames_host: np.ndarray, device, steps: int, warmup: int) -> dict:
+    """Same 512-window steps as the main arm.  `value`: windows gathered on the device from the resident audio
+    (a strided view -> [512, 24000], what `encode_batch` is given), CUDA events.  `e2e`: the reference's own
+    call `ecapa_encode_batch` (speech_encode.py:73-78): torch.from_numpy(host batch).float() -> .to(device) inside
+    encode_batch -> .squeeze(1).cpu().numpy(), wall clock around the loop."""
+    eo, model = torch_gpu_setup(state_dict, device)
+    n_windows = 1 + (audio_dev.numel() - WIN) // HOP
+    n_batches = n_windows // BATCH
+    frames_dev = audio_dev.as_strided((n_windows, WIN), (HOP, 1))
+
+    def step(i):
+        b = i % n_batches
+        with torch.inference_mode():
+            e = eo.encode_batch(model, frames_dev[b * BATCH:(b + 1) * BATCH]).squeeze(1)
+            return torch.nn.functional.normalize(e, dim=1)
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+
+    def e2e_step(i):
+        b = i % n_batches
+        with torch.inference_mode():
+            x = torch.from_numpy(np.ascontiguousarray(frames_host[b * BATCH:(b + 1) * BATCH])).float()
+            return eo.encode_batch(model, x.to(device)).squeeze(1).cpu().numpy()
+    for i in range(2):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        out = e2e_step(warmup + i)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    assert out.shape == (BATCH, 192)
+    del model
+    torch.cuda.empty_cache()
+    return {"value": BATCH / (ms * 1e-3), "unit": "embeddings/s", "ms_per_step": ms,
+            "e2e": {"value": BATCH / e2e_s, "unit": "embeddings/s", "ms_per_step": 1e3 * e2e_s,
+                    "h2d_bytes_per_step": BATCH * WIN * 4, "d2h_bytes_per_step": BATCH * 192 * 4,
+                    "api": "reference ecapa_encode_batch (speech_encode.py:73-78): np.stack-ed [512, 24000] batch from "
+                           "pageable memory -> .to(device) -> encode_batch -> .cpu().numpy()"},
+            "kind": "stock PyTorch " + torch.__version__ + " eager (cuDNN/cuBLAS/cuFFT), allow_tf32=True as "
+                    "diarization_baseline.py:20-21, f32 activations; model = oracle/ecapa_oracle.ECAPA_TDNN on the GPU",
+            "dtype": "tf32"}
+
+
+def run_torch_gpu_arm(args, rank: int, local_rank: int) -> None:
+    """--impl torch_gpu: the GPU-library comparator as its own line (rank 0 only)."""
+    if rank != 0:
+        return
+    from speech_diarization_b200.weights import random_ecapa_state_dict
+    from speech_diarization_b200 import vad
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    sd = random_ecapa_state_dict(0)
+    audio = synth_audio(AUDIO_SECONDS, 4, seed=0, device=device)
+    frames = vad.frame_audio(audio.cpu().numpy(), SR, 1500.0, 750.0)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    r = torch_gpu_bench(sd, audio, frames, device, args.steps, max(args.warmup, 3))
+    clk = clocks.stop()
+    emit({"impl": "torch_gpu", "metric": METRIC, "value": r["value"], "unit": "embeddings/s", "n_gpus": 1,
+          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": r["dtype"], "data": "synthetic",
+          "config": {"workload": WORKLOAD, "window_s": 1.5, "hop_s": 0.75, "batch": BATCH, "library": r["kind"]},
+          "clocks": clk, "e2e": r["e2e"], "gpu_launches": 0})
+
+
 # ---------------------------------------------------------------------------------- AHC leg
 def same_partition(a, b) -> bool:
     fwd, bwd = {}, {}
@@ -268,6 +357,9 @@ def ahc_leg(device, with_cpu: bool) -> dict:
                     best_aff = min(best_aff, ev[0].elapsed_time(ev[1]))
                     best_ahc = min(best_ahc, ev[1].elapsed_time(ev[2]))
             ok = same_partition(labels.cpu().numpy(), lab)
+            clustering.ahc_keep_stats(True)          # one extra, untimed run for the round / merge counters
+            clustering.ahc_average_device(dist, 1 - 0.68)
+            clustering.ahc_keep_stats(False)
             stats = clustering.ahc_last_stats()
             out[f"n{N}"] = {"affinity_ms": best_aff, "ahc_ms": best_ahc, "clusters": int(ncl.item()),
                             "labels_match_planted": bool(ok), "rnn_rounds": stats["rounds"], "merges": stats["merges"],
@@ -286,6 +378,52 @@ def ahc_leg(device, with_cpu: bool) -> dict:
             torch.cuda.empty_cache()
     out["cpu_note"] = "cpu_ms = sklearn cosine_similarity + AgglomerativeClustering (diar_diag.py:219-226) at N=5000; " \
                       "the same call at N=20000 takes ~35 s on 8 cores (BASELINE.md §2) and is not repeated here"
+    return out
+
+
+def cluster_leg(device, rank: int, world: int) -> dict:
+    """BASELINE config 3's clustering stage on N > 1 GPUs: all-gather of the N = 38 399 L2-normalised
+    window embeddings of an 8 h corpus (each rank holds its shard), row-block affinity on every rank, gather of the
+    row blocks to rank 0, AHC there, label broadcast.  Per-phase device times (CUDA events, max over ranks) and
+    whether the labels equal the single-GPU result computed on rank 0 from the same embeddings."""
+    import torch.distributed as dist
+    from speech_diarization_b200 import clustering, sharded
+    N, K = 38399, 8
+    rng = np.random.default_rng(0)
+    c = rng.standard_normal((K, 192)); c /= np.linalg.norm(c, axis=1, keepdims=True)
+    lab = rng.integers(0, K, N)
+    lo, hi = sharded.shard_range(N, rank, world)
+    # every rank draws the same stream and keeps its own rows (stands in for its embedded window shard)
+    X = (c[lab] + 0.02 * rng.standard_normal((N, 192))).astype(np.float32)
+    local = clustering.l2_normalize_device(torch.from_numpy(X[lo:hi]).to(device))
+    best = None
+    for rep in range(3):
+        t: dict = {}
+        dist.barrier(); torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        emb_all = sharded.gather_embeddings(local, N)
+        ev[1].record()
+        labels = sharded.cluster_sharded(emb_all, 0.68, timings=t)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t["allgather_embeddings"] = ev[0].elapsed_time(ev[1])
+        t["total"] = ev[0].elapsed_time(ev[2])
+        names = sorted(t)
+        v = torch.tensor([t[k] for k in names], device=device)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        t = dict(zip(names, [float(x) for x in v.tolist()]))
+        if rep and (best is None or t["total"] < best["total"]):      # rep 0 = warm-up (allocations, NCCL channels)
+            best = t
+    out = {"n": N, "world": world, "phase_ms_max_over_ranks": best,
+           "gather_bytes": {"embeddings": N * 192 * 4, "row_blocks_to_rank0": int(4 * N * N * (world - 1) / world)}}
+    if rank == 0:
+        single = clustering.cluster_embeddings_device(emb_all, 0.68)
+        torch.cuda.synchronize()
+        lab_multi = labels.cpu().numpy()
+        out["labels_match_single_gpu"] = bool(same_partition(lab_multi, single.cpu().numpy()))
+        out["labels_match_planted"] = bool(same_partition(lab_multi, lab))
+        out["clusters"] = int(len(set(lab_multi.tolist())))
     return out
 
 
@@ -424,7 +562,8 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_gpu"])
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ahc", action="store_true")
     args = ap.parse_args()
@@ -434,6 +573,9 @@ def main() -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.impl == "torch_gpu":
+        run_torch_gpu_arm(args, rank, local_rank)
         return
 
     import torch.distributed as dist
@@ -453,14 +595,19 @@ def main() -> None:
     n_batches = n_windows // BATCH                                  # 9 full batches, cycled
     sd = random_ecapa_state_dict(0)
     enc = speech_encode.EcapaEncoderB200(sd, device=device, max_batch=BATCH, max_samples=WIN)
-    emb = torch.empty((BATCH, 192), dtype=torch.float32, device=device)
-    gathered = torch.empty((world * BATCH, 192), dtype=torch.float32, device=device) if world > 1 else None
+    # every step's embeddings stay on the device; for N > 1 the run ends with ONE NCCL all-gather of the
+    # [steps * 512, 192] shard (the real pipeline gathers once per recording, sharded.embed_windows_sharded)
+    n_slots = max(args.steps, args.warmup, 1)
+    emb_all = torch.empty((n_slots * BATCH, 192), dtype=torch.float32, device=device)
+    gathered = torch.empty((world * args.steps * BATCH, 192), dtype=torch.float32, device=device) if world > 1 else None
 
-    def step(i: int) -> None:
+    def step(i: int, slot: int = 0) -> None:
         off = (i % n_batches) * BATCH * HOP
-        enc.embed_device(audio[off:], HOP, BATCH, WIN, l2_normalize=True, out=emb)
+        enc.embed_device(audio[off:], HOP, BATCH, WIN, l2_normalize=True, out=emb_all[slot * BATCH:(slot + 1) * BATCH])
+
+    def gather_run() -> None:
         if world > 1:
-            dist.all_gather_into_tensor(gathered, emb)
+            dist.all_gather_into_tensor(gathered, emb_all[:args.steps * BATCH])
 
     def barrier():
         if world > 1:
@@ -468,7 +615,8 @@ def main() -> None:
         torch.cuda.synchronize()
 
     for i in range(args.warmup):
-        step(i)
+        step(i, i)
+    gather_run()
     barrier()
 
     # ---- timed region 1: device-resident inputs ("value"); the trunk replays its CUDA graph
@@ -479,7 +627,8 @@ def main() -> None:
     barrier()
     e0.record()
     for i in range(args.steps):
-        step(args.warmup + i)
+        step(args.warmup + i, i)
+    gather_run()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -500,29 +649,48 @@ def main() -> None:
     ms_total = float(t.item())
     value = world * BATCH * args.steps / (ms_total * 1e-3)
 
-    # ---- timed region 2: end to end through the public API with HOST buffers (pinned)
+    # ---- timed region 2: end to end through the public API with HOST buffers.  Three legs, all through
+    # speech_encode.ecapa_encode_batch (H2D of the step's samples + D2H of [512,192] + a sync inside every call):
+    #   pinned_strided    vad.frame_audio view of page-locked audio (windows addressed in place, 24.6 MB / step)
+    #   pageable_strided  the same view over ordinary numpy memory
+    #   pageable_batch    a materialised np.stack-ed [512, 24000] batch in pageable memory (49 MB / step): what the
+    #                     reference's own callers pass (anti_stick_diarize.py:164-166, :423-424)
     host_audio = torch.empty(audio.shape, dtype=torch.float32, pin_memory=True)
     host_audio.copy_(audio)
     torch.cuda.synchronize()
-    frames = vad.frame_audio(host_audio.numpy(), SR, 1500.0, 750.0)         # strided view, no copy
     speech_encode.register_ecapa_state_dict(sd)          # what a user does once; using_ecapa_encoder() builds its plan
-    for i in range(2):
-        speech_encode.ecapa_encode_batch(frames[i * BATCH:(i + 1) * BATCH])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        b = (args.warmup + i) % n_batches
-        out_host = speech_encode.ecapa_encode_batch(frames[b * BATCH:(b + 1) * BATCH])
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    pageable_audio = np.array(host_audio.numpy(), copy=True)
+    frames_pinned = vad.frame_audio(host_audio.numpy(), SR, 1500.0, 750.0)         # strided view, no copy
+    frames_pageable = vad.frame_audio(pageable_audio, SR, 1500.0, 750.0)
+    batches = [np.ascontiguousarray(frames_pageable[b * BATCH:(b + 1) * BATCH]) for b in range(min(n_batches, 4))]
+
+    def e2e_leg(get_batch) -> float:
+        for i in range(2):
+            speech_encode.ecapa_encode_batch(get_batch(i))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            out_host = speech_encode.ecapa_encode_batch(get_batch(args.warmup + i))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert out_host.shape == (BATCH, 192)
+        tt = torch.tensor([dt], device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    e2e_s = e2e_leg(lambda i: frames_pinned[(i % n_batches) * BATCH:(i % n_batches + 1) * BATCH])
+    e2e_pageable_strided_s = e2e_leg(lambda i: frames_pageable[(i % n_batches) * BATCH:(i % n_batches + 1) * BATCH])
+    e2e_pageable_batch_s = e2e_leg(lambda i: batches[i % len(batches)])
     e2e_value = world * BATCH * args.steps / e2e_s
     h2d = ((BATCH - 1) * HOP + WIN) * 4
     d2h = BATCH * 192 * 4
-    assert out_host.shape == (BATCH, 192)
+    e2e_legs = {
+        "pinned_strided": {"value": e2e_value, "h2d_bytes_per_step": h2d},
+        "pageable_strided": {"value": world * BATCH * args.steps / e2e_pageable_strided_s, "h2d_bytes_per_step": h2d},
+        "pageable_batch": {"value": world * BATCH * args.steps / e2e_pageable_batch_s, "h2d_bytes_per_step": BATCH * WIN * 4,
+                           "note": "np.stack-ed [512, 24000] pageable batch, the reference callers' own convention"},
+    }
 
     if rank == 0:
         T = lib.sd_fbank_num_frames(WIN)
@@ -546,11 +714,13 @@ def main() -> None:
                        "arithmetic": "f16 operands, f32 accumulation (tcgen05 kind::f16); fbank / SE / pooling stats f32",
                        "l2_cold": "inputs larger than L2: each step reads a different 24.6 MB slice of the 230 MB "
                                   "resident audio and streams ~1.7 GB of activations (L2 = 126 MB)",
-                       "collective": "all_gather of the step's [512,192] embeddings (NCCL)" if world > 1 else "none",
+                       "collective": "one NCCL all_gather of the run's [steps*512,192] embedding shard, inside the timed region"
+                                     if world > 1 else "none",
                        "peaks": peaks_src},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "embeddings/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "speech_encode.ecapa_encode_batch(vad.frame_audio(pinned host audio)[512 windows])"},
+                    "api": "speech_encode.ecapa_encode_batch(vad.frame_audio(pinned host audio)[512 windows])",
+                    "legs": e2e_legs},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_2sm_kernel<EPI_TDNN> (tcgen05 cta_group::2, 256x256 tile per CTA pair) — "
                                                       "MFA 1x1 conv 3072->3072, 50% of the trunk's FLOPs",
@@ -565,10 +735,27 @@ def main() -> None:
             line["cpu_baseline"] = cpu_baseline(sd, host_audio.numpy())
         else:
             line["cpu_baseline"] = None
+        if world == 1 and not args.no_library_baseline:
+            try:
+                line["library_baseline"] = torch_gpu_bench(sd, audio, frames_pageable, device, min(args.steps, 10), 3)
+                line["library_baseline"]["speedup_value"] = value / line["library_baseline"]["value"]
+                line["library_baseline"]["speedup_e2e_vs_reference_call"] = (
+                    e2e_legs["pageable_batch"]["value"] / line["library_baseline"]["e2e"]["value"])
+            except Exception as e:
+                line["library_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_ahc:
             line["dense_pass"] = dense_pass_leg(enc, audio, device)
             line["ahc"] = ahc_leg(device, with_cpu=not args.no_cpu_baseline)
             line["post"] = post_leg(device, with_cpu=not args.no_cpu_baseline)
+    cluster = None
+    if world > 1 and not args.no_ahc:
+        try:
+            cluster = cluster_leg(device, rank, world)
+        except Exception as e:
+            cluster = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if rank == 0:
+        if cluster is not None:
+            line["cluster"] = cluster
         emit(line)
     if world > 1:
         dist.barrier()

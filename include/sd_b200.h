@@ -34,6 +34,7 @@ extern "C" {
 #define SD_ERR_NOMEM 4       /* device allocation failed */
 #define SD_ERR_UNSUPPORTED 5 /* valid request outside what this build implements */
 #define SD_ERR_MISSING 6     /* a required weight tensor is missing or mis-sized */
+#define SD_ERR_RANGE 7       /* an activation left the f16 range: results of the call are NaN, not silently wrong */
 
 #define SD_EMB_DIM 192  /* ecapa_annote.py:11 (self.dimension = 192) */
 #define SD_N_MELS 80
@@ -99,6 +100,14 @@ int sd_ecapa_plan_destroy(SdEcapaPlan* plan);
 int sd_ecapa_embed(SdEcapaPlan* plan, const float* wav_dev, long wav_stride, int B, int n_samples,
                    int l2_normalize, float* emb_dev, void* stream);
 
+/* The same for windows that start at ARBITRARY sample offsets of one device-resident recording: window b =
+ * wav_dev[offsets_dev[b] : offsets_dev[b] + n_samples] (offsets_dev: B x int64 on the device; the caller
+ * guarantees the windows lie inside the buffer).  One launch sequence for all the speech windows of a recording
+ * (anti_stick_diarize.py:420-427 gathers them with a Python list comprehension per batch of 128) or all the sliding
+ * windows of all the segments of scd_split_segments (:97-100, one encoder call per segment). */
+int sd_ecapa_embed_offsets(SdEcapaPlan* plan, const float* wav_dev, const long* offsets_dev, int B, int n_samples,
+                           int l2_normalize, float* emb_dev, void* stream);
+
 /* The same from HOST memory — the call behind ecapa_encode_batch(np.ndarray) (speech_encode.py:73-78) and
  * `emb = encode_batch(wav).cpu().numpy()`: wav_host / emb_host are host pointers (pinned or pageable), window
  * b = wav_host[b * wav_stride : b * wav_stride + n_samples], emb_host [B, 192] f32.  The host->device copy is
@@ -107,6 +116,16 @@ int sd_ecapa_embed(SdEcapaPlan* plan, const float* wav_dev, long wav_stride, int
  * the stream is synchronised before returning (the reference's call ends with the same implicit sync). */
 int sd_ecapa_embed_host(SdEcapaPlan* plan, const float* wav_host, long wav_stride, int B, int n_samples,
                         int l2_normalize, float* emb_host, void* stream);
+/* Pageable wav_host (ordinary numpy memory, what the reference's callers pass) is staged through a page-locked
+ * ring filled by a few copy threads (SD_ECAPA_HOST_THREADS, default 6), so the transfer is pipelined instead of
+ * a blocking driver-staged copy; page-locked memory is read by the copy engine directly.
+ * Returns SD_ERR_RANGE (and NaN embeddings) when an activation left the f16 range — see sd_ecapa_overflow. */
+
+/* Activations are stored as f16.  A value beyond +-65504 (a checkpoint with an unusually large BatchNorm scale) is
+ * saturated, never turned into inf, and raises a flag: the embeddings of that forward are written as NaN so the
+ * failure is loud on the asynchronous device path too.  This call synchronises `stream` and reports (and, with
+ * reset != 0, clears) the sticky flag. */
+int sd_ecapa_overflow(SdEcapaPlan* plan, int reset, int* flag_out, void* stream);
 
 /* Same trunk from precomputed features feats_dev [B, T, 80] f32 (already
  * normalised); used by the parity tests to isolate the trunk. */
@@ -257,6 +276,49 @@ int sd_morph_open_close_u8(const uint8_t* mask_dev, int n, int open_w, int close
 size_t sd_mask_segments_workspace_bytes(int n);
 int sd_mask_segments_i32(const uint8_t* mask_dev, int n, int min_speech_frames, int min_gap_frames,
                          int32_t* seg_dev, int32_t* count_dev, void* workspace_dev, void* stream);
+
+/* ---------------------------------------------- dense-pass operators (f2) ---
+ * The operators either side of the embedding kernels in anti_stick_diarize.py's SCD and frame-reassignment passes. */
+
+/* scd_split_segments (anti_stick_diarize.py:102-116) for ALL segments at once.  emb_dev [total, D] f32 holds the
+ * sliding-window embeddings of segment s in rows seg_off_dev[s] .. seg_off_dev[s+1] (int32, n_segments + 1
+ * entries).  Per segment: d_i = 1 - cos(e_i, e_{i+1}) (denominator + 1e-8), z = (d - mean(d)) / std(d) when
+ * std > 1e-6 else d, and peak_dev[seg_off[s] + i] = 1 where scipy.signal.find_peaks(z, height=thr) has a peak
+ * (strict local maxima and the floor-middle of flat tops; never the first or last distance).  z_dev [total] f32
+ * receives z (scratch the caller may inspect).  One CTA per segment. */
+int sd_scd_peaks(const float* emb_dev, int D, const int32_t* seg_off_dev, int n_segments, float thr,
+                 float* z_dev, uint8_t* peak_dev, void* stream);
+
+/* speaker_centroids (anti_stick_diarize.py:333-349): out_dev[k] = mean of the rows with labels_dev[i] ==
+ * spk_ids_dev[k], divided by (its norm + 1e-8).  D <= 256. */
+int sd_speaker_centroids(const float* emb_dev, const int32_t* labels_dev, int N, int D,
+                         const int32_t* spk_ids_dev, int K, float* out_dev, void* stream);
+
+/* full_dev[valid_dev[i]] = label_map_dev ? label_map_dev[labels_dev[i]] : labels_dev[i]  for i < m
+ * (anti_stick_diarize.py:374-375, :435; the caller pre-fills full_dev with -1). */
+int sd_scatter_labels(const int32_t* valid_dev, const int32_t* labels_dev, const int32_t* label_map_dev, int m,
+                      int32_t* full_dev, void* stream);
+
+/* _labels_to_segments (anti_stick_diarize.py:377-386): run-length encoding of labels_dev[0, n) (-1 = no speech).
+ * A run [i, j) of speaker k becomes start = window_starts_dev[i] / sr, end = j < n ? window_starts_dev[j] / sr :
+ * max_t (f64, the reference's own expressions) and is kept when k != -1 and end > start.
+ * run_idx_dev [count][3] int32 = (i, j, k); run_t_dev [count][2] f64 = (start, end); count_dev [1];
+ * scratch_dev: n int32.  Capacity n rows each.  Single CTA of block scans (n <= a few 10^5 windows). */
+int sd_label_runs(const int32_t* labels_dev, int n, const int64_t* window_starts_dev, double sr, double max_t,
+                  int32_t* scratch_dev, int32_t* run_idx_dev, double* run_t_dev, int32_t* count_dev, void* stream);
+
+/* merge_adjacent (anti_stick_diarize.py:464-475) on segments (seg_t_dev [n][2] f64 start/end, speaker of segment k
+ * at spk_dev[k * spk_stride]): segment k joins its predecessor when the speakers are equal and
+ * start[k] - end[k-1] <= gap.  group_dev [count][2] int32 = (first, last) segment of each merged group.
+ * n is taken from *n_dev when n_dev != NULL (chained behind sd_label_runs without a host round trip; pass the
+ * capacity as n). */
+int sd_merge_adjacent(const double* seg_t_dev, const int32_t* spk_dev, int spk_stride, int n, const int32_t* n_dev,
+                      double gap, int32_t* group_dev, int32_t* count_dev, void* stream);
+
+/* Zero-padded batch of variable-length snippets of one device-resident recording (embed_segments,
+ * anti_stick_diarize.py:162-166): out_dev[b, i] = audio_dev[start_dev[b] + i] for i < len_dev[b], else 0. */
+int sd_gather_pad_f32(const float* audio_dev, const int64_t* start_dev, const int32_t* len_dev, int B, int max_len,
+                      float* out_dev, void* stream);
 
 /* ------------------------------------------------------------ debug / test ---
  * Raw tensor-core GEMM used by the unit tests of the tcgen05 kernel:

@@ -59,12 +59,12 @@ def fbank_speechbrain(wavs: torch.Tensor, mean_norm: bool = True) -> torch.Tenso
     """wavs [B, n] f32 -> [B, T, 80]: STFT(Hamming 400/160, zero centre pad) -> power ->
     mel -> dB (top_db 80 per utterance) -> sentence mean normalisation (App. A.1)."""
     wavs = wavs.float()
-    window = torch.hamming_window(400)
+    window = torch.hamming_window(400, device=wavs.device)
     spec = torch.stft(wavs, n_fft=400, hop_length=160, win_length=400, window=window, center=True,
                       pad_mode="constant", normalized=False, onesided=True, return_complex=True)
     power = spec.real.pow(2) + spec.imag.pow(2)          # [B, 201, T]
     power = power.transpose(1, 2)                        # [B, T, 201]
-    fb = speechbrain_filterbank_matrix()
+    fb = speechbrain_filterbank_matrix().to(wavs.device)
     mel = torch.matmul(power, fb)
     x_db = 10.0 * torch.log10(torch.clamp(mel, min=1e-10))
     floor = x_db.amax(dim=(-2, -1)) - 80.0

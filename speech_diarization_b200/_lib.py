@@ -29,7 +29,9 @@ SIGNATURES = {
     "sd_ecapa_plan_create": (c_int, [POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_int, c_int, POINTER(c_void_p)]),
     "sd_ecapa_plan_destroy": (c_int, [c_void_p]),
     "sd_ecapa_embed": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sd_ecapa_embed_offsets": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sd_ecapa_embed_host": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sd_ecapa_overflow": (c_int, [c_void_p, c_int, POINTER(c_int), c_void_p]),
     "sd_ecapa_forward_feats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sd_ecapa_debug_fetch": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int), c_void_p]),
     "sd_ecapa_profile": (c_int, [c_void_p, c_int]),
@@ -58,6 +60,12 @@ SIGNATURES = {
     "sd_morph_open_close_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sd_mask_segments_workspace_bytes": (c_size_t, [c_int]),
     "sd_mask_segments_i32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sd_scd_peaks": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "sd_speaker_centroids": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "sd_scatter_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "sd_label_runs": (c_int, [c_void_p, c_int, c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sd_merge_adjacent": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+    "sd_gather_pad_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sd_debug_gemm_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

@@ -49,18 +49,28 @@ def ahc_average_device(dist: torch.Tensor, threshold: float):
     with torch.cuda.device(dist.device):
         _lib.check(lib.sd_ahc_average_f32(dist.data_ptr(), N, float(threshold), labels.data_ptr(),
                                           ncl.data_ptr(), ws.data_ptr(), _lib.stream_ptr()), "sd_ahc_average_f32")
-    ahc_average_device.last_workspace = (ws, N)
+    if _KEEP_STATS:
+        # debug / bench only: reading the two counters synchronises.  The 8 N^2-byte workspace itself is NOT kept
+        # alive past this call (it used to be, 3.2 GB at N = 20k)
+        import ctypes
+        r, m = ctypes.c_int32(0), ctypes.c_int32(0)
+        _lib.check(lib.sd_ahc_read_stats(ws.data_ptr(), N, ctypes.byref(r), ctypes.byref(m)), "sd_ahc_read_stats")
+        ahc_average_device.last_stats = {"rounds": r.value, "merges": m.value}
     return labels, ncl
 
 
+_KEEP_STATS = False
+
+
+def ahc_keep_stats(enable: bool) -> None:
+    """Record {"rounds", "merges"} of every following ahc_average_device call (costs a synchronisation per call)."""
+    global _KEEP_STATS
+    _KEEP_STATS = bool(enable)
+
+
 def ahc_last_stats() -> dict:
-    """{"rounds", "merges"} of the most recent ahc_average_device call (synchronises)."""
-    import ctypes
-    lib = _lib.load()
-    ws, N = ahc_average_device.last_workspace
-    r, m = ctypes.c_int32(0), ctypes.c_int32(0)
-    _lib.check(lib.sd_ahc_read_stats(ws.data_ptr(), N, ctypes.byref(r), ctypes.byref(m)), "sd_ahc_read_stats")
-    return {"rounds": r.value, "merges": m.value}
+    """{"rounds", "merges"} of the most recent ahc_average_device call made while ahc_keep_stats(True)."""
+    return dict(getattr(ahc_average_device, "last_stats", {"rounds": -1, "merges": -1}))
 
 
 def window_argmax_device(x: torch.Tensor, cent: torch.Tensor):

@@ -97,11 +97,12 @@ extern "C" size_t sd_affinity_workspace_bytes(int N, int D) {
 extern "C" int sd_cosine_distance_rowblock(const float* emb_dev, int N, int D, int row0, int rows,
                                            float* out_dev, double* out_f64_dev, void* workspace_dev,
                                            void* stream) {
-  if (!emb_dev || !out_dev || !workspace_dev || N < 1 || D < 64 || D % 64 || D > 512 || row0 < 0 ||
-      rows < 0 || row0 + rows > N)
+  if (N < 1 || D < 64 || D % 64 || D > 512 || row0 < 0 || rows < 0 || row0 + rows > N)
     return fail(SD_ERR_ARG, "sd_cosine_distance_rowblock: bad arguments N=%d D=%d row0=%d rows=%d", N, D,
                 row0, rows);
-  if (rows == 0) return SD_OK;
+  if (rows == 0) return SD_OK;   // an empty row block (a rank beyond the last shard) has no output buffer to check
+  if (!emb_dev || !out_dev || !workspace_dev)
+    return fail(SD_ERR_ARG, "sd_cosine_distance_rowblock: NULL buffer (N=%d rows=%d)", N, rows);
   if (3 * (D / 64) > MAX_KITERS) return fail(SD_ERR_ARG, "D too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __half* xs = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~uintptr_t(255));

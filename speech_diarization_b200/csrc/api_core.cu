@@ -14,6 +14,7 @@ extern "C" const char* sd_status_string(int s) {
     case SD_ERR_NOMEM: return "out of device memory";
     case SD_ERR_UNSUPPORTED: return "unsupported";
     case SD_ERR_MISSING: return "missing weight tensor";
+    case SD_ERR_RANGE: return "activation out of f16 range";
   }
   return "unknown";
 }

@@ -28,6 +28,7 @@
 #include "ecapa_kernels.cuh"
 #include "fbank.cuh"
 #include "gemm_host.cuh"
+#include "host_stage.cuh"
 #include "res2net_fused.cuh"
 #include "sd_status.h"
 
@@ -54,7 +55,8 @@ struct TdnnW {       // one TDNNBlock: conv weight (f16, [Cout, taps*CinP]) + fo
 
 struct BlockW {
   TdnnW tdnn1, res[7], tdnn2;
-  float *se_w1 = nullptr, *se_b1 = nullptr, *se_w2t = nullptr, *se_b2 = nullptr;
+  __half *se_w1h = nullptr, *se_w2th = nullptr;   // SE weights as f16: conv1 [SE][C1], conv2 transposed [SE][C1]
+  float *se_b1 = nullptr, *se_b2 = nullptr;
   int dil = 2;
 };
 
@@ -65,7 +67,8 @@ struct Program {     // launch parameters for one (B, T) shape
   GemmParams* chain_dev = nullptr;  // device copy of [3][9]: tdnn1, 7 x Res2Net, tdnn2 per block
   Res2Params r2[3];                 // the 7 Res2Net convs of a block as one launch (res2net_fused.cuh)
   bool r2_ok = false;               // shape fits the fused kernel (16 <= T, T + 2*dil <= 168)
-  bool colsum_ok = false;           // Tp >= 128: SE / ASP time statistics come out of the GEMM write-outs
+  bool colsum_ok = false;           // SE / ASP time statistics come out of the GEMM write-outs
+  int cs_group = 128;               // rows per statistics group: gcd(128, Tp)
   cudaGraphExec_t graph = nullptr;  // captured trunk (block0 .. FC) for this shape
   int graph_launches = 0;
   int runs = 0;
@@ -101,6 +104,9 @@ struct SdEcapaPlan {
   float *raw = nullptr, *se_mean = nullptr, *se_hid = nullptr, *se_scale = nullptr, *stats = nullptr;
   float *cs_se = nullptr, *cs_mfa = nullptr, *cq_mfa = nullptr;  // per (m block, window slot) column sums from the GEMM write-outs
   float *uttbias = nullptr, *pooled = nullptr, *emb_tmp = nullptr, *ctx_part = nullptr;
+  int* oflow = nullptr;       // [0] an activation of the current forward left the f16 range (reset per forward),
+                              // [1] sticky copy for the host (sd_ecapa_overflow / sd_ecapa_embed_host)
+  int* oflow_host = nullptr;  // page-locked landing word for [1]
   __half *stats_h = nullptr, *pooled_h = nullptr;
   std::map<std::pair<int, int>, Program> programs;
   Program* last = nullptr;
@@ -137,6 +143,8 @@ struct SdEcapaPlan {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[8] = {};
   cudaEvent_t start_ev = nullptr;
+  StagingRing* ring = nullptr;   // pinned staging ring + copy threads for pageable callers (host_stage.cuh)
+  bool ring_failed = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   int forwards_profiled = 0;
@@ -248,6 +256,7 @@ int setup_tdnn_gemm(GemmParams& P, const __half* A, long rows, int a_cols, int l
   E.bias = W.bias;
   E.scale = W.scale;
   E.shift = W.shift;
+  E.cs_group = pr.cs_group;
   return SD_OK;
 }
 
@@ -283,6 +292,8 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   pr.T = T;
   pr.Tp = tp_of(T);
   pr.rows = (long)B * pr.Tp;
+  pr.cs_group = 128;
+  while (pr.Tp % pr.cs_group) pr.cs_group >>= 1;   // gcd(128, Tp); Tp is a multiple of 16
   const long R = pr.rows;
   // block0: k = 5 over the 128-padded mel channels
   SD_TRY(setup_tdnn_gemm(pr.block0, p->feats, R, FEAT_P, FEAT_P, p->w0, C1, 5 * FEAT_P, 256, FEAT_P,
@@ -344,10 +355,11 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
       Q.dil = bw.dil;
       Q.idesc = make_idesc_f16(SUB, 0);
       Q.idesc_t1 = make_idesc_f16(32, 0);
+      Q.oflow = p->oflow;
     }
     SD_TRY(setup_tdnn_gemm(pr.tdnn2[b], p->v, R, C1, C1, bw.tdnn2, C1, C1, 256, C1, 1, 1, 0, pr,
                            p->w, C1, 0, 0, p->use_mc || p->use_2sm));
-    pr.colsum_ok = p->use_colsum && pr.Tp >= 128;
+    pr.colsum_ok = p->use_colsum;
     if (pr.colsum_ok) pr.tdnn2[b].epi.colsum = p->cs_se;
     SD_TRY(enable_tma_out(p, pr.tdnn2[b]));
   }
@@ -444,6 +456,14 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     P.epi.pooled_h = p->pooled_h;
     P.epi.C = C3;
   }
+  {
+    GemmParams* all[] = {&pr.block0, &pr.mfa, &pr.att};
+    for (GemmParams* g : all) g->epi.oflow = p->oflow;
+    for (int b = 0; b < 3; ++b) {
+      pr.tdnn1[b].epi.oflow = pr.tdnn2[b].epi.oflow = p->oflow;
+      for (int i = 0; i < 7; ++i) pr.res[b][i].epi.oflow = pr.resc[b][i].epi.oflow = p->oflow;
+    }
+  }
   if (p->use_2sm) {
     pr.block0.idesc = make_idesc_f16(256, 0, 256);
     pr.mfa.idesc = make_idesc_f16(256, 0, 256);
@@ -477,8 +497,8 @@ GemmParams sub_rows(const GemmParams& G, long row0, long nrows) {
   E.M_rows = static_cast<int>(nrows);
   E.out = static_cast<__half*>(E.out) + row0 * E.ld_out;
   if (E.out2) E.out2 += row0 * E.ld_out2;
-  if (E.colsum) E.colsum += (row0 / BM) * 2 * E.N_cols;
-  if (E.colsq) E.colsq += (row0 / BM) * 2 * E.N_cols;
+  if (E.colsum) E.colsum += (row0 / BM) * (BM / E.cs_group) * E.N_cols;
+  if (E.colsq) E.colsq += (row0 / BM) * (BM / E.cs_group) * E.N_cols;
   E.flags &= ~EF_TMA_OUT;   // the output tensor maps describe the whole tensor
   return S;
 }
@@ -609,7 +629,10 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st, bool skip_front = f
   const int B = pr.B, T = pr.T, Tp = pr.Tp;
   const long R = pr.rows;
   mark(p, st);  // end of fbank / start of block0
-  if (!skip_front) SD_TRY(launch_big(p, pr.block0, st));
+  if (!skip_front) {
+    SD_CUDA_OK(cudaMemsetAsync(p->oflow, 0, sizeof(int), st));   // per-forward overflow flag (a graph node on replay)
+    SD_TRY(launch_big(p, pr.block0, st));
+  }
   for (int b = 0; b < 3; ++b) {
     const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
     const int ld_in = b == 0 ? C1 : C3;
@@ -637,28 +660,28 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st, bool skip_front = f
       SD_TRY(launch_big(p, pr.tdnn2[b], st));
     }
     mark(p, st);
-    if (pr.colsum_ok)
-      SD_CUDA_OK(launch_pdl(colstats_finish_kernel, dim3(C1 / 256, B), dim3(256), 0, st, p->cs_se, nullptr,
-                            p->blk[b].tdnn2.shift, C1, Tp, T, pr.tdnn2[b].num_m_blocks, p->se_mean, C1, nullptr, nullptr));
-    else
+    // squeeze-excitation gate in one launch: finish the per-window column sums tdnn2's write-out left (or take
+    // the mean of the separate pass), 1024 -> 128 -> 1024 MLP, sigmoid
+    if (!pr.colsum_ok)
       SD_CUDA_OK(launch_pdl(time_mean_kernel, dim3(C1 / 256, B), dim3(128), 0, st, p->w, C1, Tp, T, HALO, C1, p->se_mean));
-    SD_CUDA_OK(launch_pdl(se_hidden_kernel, dim3((B + SE_U - 1) / SE_U, SE / 32), dim3(256), SE_U * C1 * sizeof(float), st,
-                          p->se_mean, p->blk[b].se_w1, p->blk[b].se_b1, B, C1, SE, p->se_hid));
-    SD_CUDA_OK(launch_pdl(se_scale_kernel, dim3((B + SE_U - 1) / SE_U, C1 / 256), dim3(256), 0, st, p->se_hid,
-                          p->blk[b].se_w2t, p->blk[b].se_b2, B, C1, SE, p->se_scale));
+    SD_CUDA_OK(launch_pdl(se_gate_kernel, dim3((B + SEG - 1) / SEG), dim3(256), 0, st,
+                          pr.colsum_ok ? p->cs_se : static_cast<const float*>(nullptr), p->blk[b].tdnn2.shift, Tp, T,
+                          pr.cs_group, pr.colsum_ok ? static_cast<const float*>(nullptr) : p->se_mean, p->blk[b].se_w1h,
+                          p->blk[b].se_b1, p->blk[b].se_w2th, p->blk[b].se_b2, B,
+                          pr.colsum_ok ? p->se_mean : static_cast<float*>(nullptr), p->se_scale));
     const long vecs = R * (C1 / 8);
     const int grid = (int)((vecs + 255) / 256 < 148L * 16 ? (vecs + 255) / 256 : 148L * 16);
     SD_CUDA_OK(launch_pdl(se_apply_kernel, dim3(grid), dim3(256), 0, st, p->w, C1, p->se_scale, in, ld_in,
-                          p->cat + (size_t)b * C1, C3, R, Tp, C1, p->use_l2_order ? 1 : 0));
+                          p->cat + (size_t)b * C1, C3, R, Tp, C1, p->use_l2_order ? 1 : 0, p->oflow));
     SD_CUDA_OK(cudaGetLastError());
-    count_launch(4);
+    count_launch(pr.colsum_ok ? 2 : 3);
   }
   mark(p, st);
   SD_TRY(launch_big(p, pr.mfa, st));
   mark(p, st);
   if (pr.colsum_ok)
     SD_CUDA_OK(launch_pdl(colstats_finish_kernel, dim3(C3 / 256, B), dim3(256), 0, st, p->cs_mfa, p->cq_mfa, p->wmfa.shift,
-                          C3, Tp, T, pr.mfa.num_m_blocks, p->stats, 2 * C3, p->stats + C3, p->stats_h));
+                          C3, Tp, T, pr.cs_group, p->stats, 2 * C3, p->stats + C3, p->stats_h));
   else
     SD_CUDA_OK(launch_pdl(time_mean_std_kernel, dim3(C3 / 256, B), dim3(128), 0, st, p->h, C3, Tp, T, HALO, C3, p->stats,
                           p->stats_h));
@@ -715,7 +738,8 @@ int run_trunk(SdEcapaPlan* p, Program& pr, int l2_normalize, float* emb, cudaStr
     SD_TRY(trunk_body(p, pr, st, skip_front));
   }
   ++runs;
-  fc_finish_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->emb_tmp, p->ksplit, (long)B * EMB, B, EMB, l2_normalize, 1e-8f, emb);
+  fc_finish_kernel<<<(B + 7) / 8, 256, 0, st>>>(p->emb_tmp, p->ksplit, (long)B * EMB, B, EMB, l2_normalize, 1e-8f, emb,
+                                                p->oflow, p->oflow + 1);
   SD_CUDA_OK(cudaGetLastError());
   count_launch(1);
   mark(p, st);  // end of fc
@@ -771,17 +795,18 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
         SD_TRY(load_tdnn(p, sd, pre + ".res2net_block.blocks." + std::to_string(i), SUB, SUB, 3, SUB, SUB,
                          &bw.res[i]));
       SD_TRY(load_tdnn(p, sd, pre + ".tdnn2", C1, C1, 1, C1, C1, &bw.tdnn2));
-      const float *w1, *b1, *w2, *b2;
+      const float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
       SD_TRY(sd.get(pre + ".se_block.conv1.conv.weight", (int64_t)SE * C1, &w1));
       SD_TRY(sd.get(pre + ".se_block.conv1.conv.bias", SE, &b1));
       SD_TRY(sd.get(pre + ".se_block.conv2.conv.weight", (int64_t)C1 * SE, &w2));
       SD_TRY(sd.get(pre + ".se_block.conv2.conv.bias", C1, &b2));
-      std::vector<float> w2t((size_t)SE * C1);
+      std::vector<__half> w1h((size_t)SE * C1), w2th((size_t)SE * C1);
+      for (size_t i = 0; i < w1h.size(); ++i) w1h[i] = __float2half_rn(w1[i]);
       for (int c = 0; c < C1; ++c)
-        for (int j = 0; j < SE; ++j) w2t[(size_t)j * C1 + c] = w2[(size_t)c * SE + j];
-      SD_TRY(upload(p, &bw.se_w1, std::vector<float>(w1, w1 + (size_t)SE * C1)));
+        for (int j = 0; j < SE; ++j) w2th[(size_t)j * C1 + c] = __float2half_rn(w2[(size_t)c * SE + j]);
+      SD_TRY(upload(p, &bw.se_w1h, w1h));
       SD_TRY(upload(p, &bw.se_b1, std::vector<float>(b1, b1 + SE)));
-      SD_TRY(upload(p, &bw.se_w2t, w2t));
+      SD_TRY(upload(p, &bw.se_w2th, w2th));
       SD_TRY(upload(p, &bw.se_b2, std::vector<float>(b2, b2 + C1)));
     }
     SD_TRY(load_tdnn(p, sd, "mfa", C3, C3, 1, C3, C3, &p->wmfa));
@@ -844,11 +869,13 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
     SD_TRY(dev_alloc(p, (void**)&p->se_mean, MB * C1 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->se_scale, MB * C1 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->se_hid, MB * SE * 4, true));
+    SD_TRY(dev_alloc(p, (void**)&p->oflow, 2 * sizeof(int), true));
     {
       const size_t mblocks = (size_t)(p->max_rows + BM - 1) / BM + 1;
-      SD_TRY(dev_alloc(p, (void**)&p->cs_se, mblocks * 2 * C1 * 4, true));
-      SD_TRY(dev_alloc(p, (void**)&p->cs_mfa, mblocks * 2 * C3 * 4, true));
-      SD_TRY(dev_alloc(p, (void**)&p->cq_mfa, mblocks * 2 * C3 * 4, true));
+      // one partial sum per group of gcd(128, Tp) >= 16 rows: at most 8 groups per 128-row block
+      SD_TRY(dev_alloc(p, (void**)&p->cs_se, mblocks * 8 * C1 * 4, true));
+      SD_TRY(dev_alloc(p, (void**)&p->cs_mfa, mblocks * 8 * C3 * 4, true));
+      SD_TRY(dev_alloc(p, (void**)&p->cq_mfa, mblocks * 8 * C3 * 4, true));
     }
     SD_TRY(dev_alloc(p, (void**)&p->stats, MB * 2 * C3 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->uttbias, MB * ATT * 4, true));
@@ -882,6 +909,8 @@ extern "C" int sd_ecapa_plan_destroy(SdEcapaPlan* p) {
   if (p->h2d_buf) cudaFree(p->h2d_buf);
   if (p->emb_stage) cudaFree(p->emb_stage);
   if (p->emb_pinned) cudaFreeHost(p->emb_pinned);
+  if (p->oflow_host) cudaFreeHost(p->oflow_host);
+  delete p->ring;
   for (auto& kv : p->programs) {
     if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
     if (kv.second.graph_tail) cudaGraphExecDestroy(kv.second.graph_tail);
@@ -903,6 +932,21 @@ extern "C" int sd_ecapa_embed(SdEcapaPlan* p, const float* wav_dev, long wav_str
   mark(p, st);  // start of fbank
   SD_TRY(fbank_launch(wav_dev, wav_stride, B, n_samples, SD_FBANK_SPEECHBRAIN, 1, p->raw, nullptr,
                       p->feats, pr->Tp, HALO, st));
+  return run_trunk(p, *pr, l2_normalize, emb_dev, st);
+}
+
+extern "C" int sd_ecapa_embed_offsets(SdEcapaPlan* p, const float* wav_dev, const long* offsets_dev, int B,
+                                      int n_samples, int l2_normalize, float* emb_dev, void* stream) {
+  if (!p || !wav_dev || !offsets_dev || !emb_dev) return fail(SD_ERR_ARG, "sd_ecapa_embed_offsets: NULL argument");
+  if (n_samples < 400) return fail(SD_ERR_ARG, "sd_ecapa_embed_offsets: n_samples=%d < 400", n_samples);
+  const int T = 1 + n_samples / 160;
+  SD_TRY(check_shape(p, B, T));
+  Program* pr = nullptr;
+  SD_TRY(build_program(p, B, T, &pr));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mark(p, st);  // start of fbank
+  SD_TRY(fbank_launch(wav_dev, 0, B, n_samples, SD_FBANK_SPEECHBRAIN, 1, p->raw, nullptr, p->feats, pr->Tp, HALO, st,
+                      offsets_dev));
   return run_trunk(p, *pr, l2_normalize, emb_dev, st);
 }
 
@@ -960,36 +1004,110 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
   const bool pipe_env = pipe_str && atoi(pipe_str) != 0;
   if (!pr->front_built) SD_TRY(build_front(p, *pr));
   const bool piped = pipe_env && chunks == Program::NFRONT && pr->front_ok && !p->profile;
-  size_t copied = 0;  // samples of the span already queued (windows overlap when stride < n)
-  for (int c = 0; c < chunks; ++c) {
-    const int b0 = static_cast<int>(static_cast<long>(B) * c / chunks);
-    const int b1 = static_cast<int>(static_cast<long>(B) * (c + 1) / chunks);
-    if (b1 <= b0) continue;
-    static const bool nocopy = getenv("SD_DEBUG_NOCOPY") != nullptr;  // TIMING PROBE ONLY: leaves the staging as it is
-    if (nocopy) {
-    } else if (wav_stride <= n_samples) {
-      const size_t end = static_cast<size_t>(b1 - 1) * wav_stride + n_samples;
-      SD_CUDA_OK(cudaMemcpyAsync(p->h2d_buf + copied, wav_host + copied, (end - copied) * sizeof(float),
-                                 cudaMemcpyHostToDevice, p->copy_stream));
-      copied = end;
-    } else {   // gaps between windows belong to the caller: copy the windows only
-      SD_CUDA_OK(cudaMemcpy2DAsync(p->h2d_buf + static_cast<size_t>(b0) * wav_stride, wav_stride * sizeof(float),
-                                   wav_host + static_cast<size_t>(b0) * wav_stride, wav_stride * sizeof(float),
-                                   static_cast<size_t>(n_samples) * sizeof(float), b1 - b0, cudaMemcpyHostToDevice,
-                                   p->copy_stream));
-    }
+  if (piped) SD_CUDA_OK(cudaMemsetAsync(p->oflow, 0, sizeof(int), st));   // the front runs before trunk_body's own reset
+  static const bool nocopy = getenv("SD_DEBUG_NOCOPY") != nullptr;  // TIMING PROBE ONLY: leaves the staging as it is
+  // chunk c = windows [B*c/chunks, B*(c+1)/chunks): once its samples are on the device, its fbank kernels (and, when
+  // piped, the front of the trunk) are queued behind the copy event
+  auto chunk_range = [&](int c, int* b0, int* b1) {
+    *b0 = static_cast<int>(static_cast<long>(B) * c / chunks);
+    *b1 = static_cast<int>(static_cast<long>(B) * (c + 1) / chunks);
+  };
+  auto launch_chunk = [&](int c) -> int {
+    int b0, b1;
+    chunk_range(c, &b0, &b1);
+    if (b1 <= b0) return SD_OK;
     SD_CUDA_OK(cudaEventRecord(p->copy_ev[c], p->copy_stream));
     SD_CUDA_OK(cudaStreamWaitEvent(st, p->copy_ev[c], 0));
     SD_TRY(fbank_launch(p->h2d_buf + static_cast<size_t>(b0) * wav_stride, wav_stride, b1 - b0, n_samples,
                         SD_FBANK_SPEECHBRAIN, 1, p->raw + static_cast<size_t>(b0) * T * 80, nullptr,
                         p->feats + static_cast<size_t>(b0) * pr->Tp * FEAT_P, pr->Tp, HALO, st));
     if (piped) SD_TRY(front_body(p, *pr, c, st));
+    return SD_OK;
+  };
+  // Page-locked caller memory is read by the copy engine directly.  Pageable memory (what the reference's callers
+  // pass) goes through the pinned staging ring filled by copy threads, so the transfer is asynchronous and
+  // pipelined instead of a driver-staged blocking cudaMemcpy.  SD_ECAPA_STAGING=0 restores the plain copy.
+  bool staged = false;
+  if (!nocopy && wav_stride <= n_samples) {
+    static const bool staging_on = [] { const char* e = getenv("SD_ECAPA_STAGING"); return !e || atoi(e) != 0; }();
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, wav_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned && staging_on && !p->ring_failed && span * sizeof(float) >= (size_t(1) << 20)) {
+      if (!p->ring) {
+        static const int n_thr = [] { const char* e = getenv("SD_ECAPA_HOST_THREADS"); return e ? atoi(e) : 6; }();
+        p->ring = new StagingRing;
+        if (!p->ring->init(n_thr)) {
+          delete p->ring;
+          p->ring = nullptr;
+          p->ring_failed = true;
+        }
+      }
+      staged = p->ring != nullptr;
+    }
+  }
+  if (staged) {
+    int next = 0, rc = SD_OK;
+    const cudaError_t e = p->ring->upload(
+        reinterpret_cast<const char*>(wav_host), reinterpret_cast<char*>(p->h2d_buf), span * sizeof(float), p->copy_stream,
+        [&](size_t done_bytes) {
+          while (rc == SD_OK && next < chunks) {
+            int b0, b1;
+            chunk_range(next, &b0, &b1);
+            const size_t end = b1 > b0 ? (static_cast<size_t>(b1 - 1) * wav_stride + n_samples) * sizeof(float) : 0;
+            if (end > done_bytes) break;
+            rc = launch_chunk(next++);
+          }
+        });
+    if (e != cudaSuccess) return fail(SD_ERR_CUDA, "staged upload failed: %s", cudaGetErrorString(e));
+    SD_TRY(rc);
+  } else {
+    size_t copied = 0;  // samples of the span already queued (windows overlap when stride < n)
+    for (int c = 0; c < chunks; ++c) {
+      int b0, b1;
+      chunk_range(c, &b0, &b1);
+      if (b1 <= b0) continue;
+      if (nocopy) {
+      } else if (wav_stride <= n_samples) {
+        const size_t end = static_cast<size_t>(b1 - 1) * wav_stride + n_samples;
+        SD_CUDA_OK(cudaMemcpyAsync(p->h2d_buf + copied, wav_host + copied, (end - copied) * sizeof(float),
+                                   cudaMemcpyHostToDevice, p->copy_stream));
+        copied = end;
+      } else {   // gaps between windows belong to the caller: copy the windows only
+        SD_CUDA_OK(cudaMemcpy2DAsync(p->h2d_buf + static_cast<size_t>(b0) * wav_stride, wav_stride * sizeof(float),
+                                     wav_host + static_cast<size_t>(b0) * wav_stride, wav_stride * sizeof(float),
+                                     static_cast<size_t>(n_samples) * sizeof(float), b1 - b0, cudaMemcpyHostToDevice,
+                                     p->copy_stream));
+      }
+      SD_TRY(launch_chunk(c));
+    }
   }
   SD_TRY(run_trunk(p, *pr, l2_normalize, p->emb_stage, st, piped));
   const size_t emb_bytes = static_cast<size_t>(B) * EMB * sizeof(float);
   SD_CUDA_OK(cudaMemcpyAsync(p->emb_pinned ? p->emb_pinned : emb_host, p->emb_stage, emb_bytes, cudaMemcpyDeviceToHost, st));
+  if (!p->oflow_host && cudaHostAlloc(reinterpret_cast<void**>(&p->oflow_host), sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    p->oflow_host = nullptr;
+  }
+  if (p->oflow_host) SD_CUDA_OK(cudaMemcpyAsync(p->oflow_host, p->oflow + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   SD_CUDA_OK(cudaStreamSynchronize(st));
   if (p->emb_pinned) memcpy(emb_host, p->emb_pinned, emb_bytes);
+  if (p->oflow_host && *p->oflow_host != 0) {
+    cudaMemsetAsync(p->oflow + 1, 0, sizeof(int), st);
+    return fail(SD_ERR_RANGE, "sd_ecapa_embed_host: an activation left the f16 range (|x| > 65504) and was saturated; "
+                              "the embeddings of this call are NaN");
+  }
+  return SD_OK;
+}
+
+extern "C" int sd_ecapa_overflow(SdEcapaPlan* p, int reset, int* flag_out, void* stream) {
+  if (!p || !flag_out) return fail(SD_ERR_ARG, "sd_ecapa_overflow: NULL argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int v = 0;
+  SD_CUDA_OK(cudaMemcpyAsync(&v, p->oflow + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SD_CUDA_OK(cudaStreamSynchronize(st));
+  if (reset && v) SD_CUDA_OK(cudaMemsetAsync(p->oflow + 1, 0, sizeof(int), st));
+  *flag_out = v;
   return SD_OK;
 }
 

@@ -101,30 +101,34 @@ time_mean_std_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H,
   o[C + c + 1] = d1;
   if (stats_h) {  // f16 copy: A operand of the context-bias GEMM
     __half* oh = stats_h + static_cast<size_t>(b) * 2 * C;
-    *reinterpret_cast<__half2*>(oh + c) = __floats2half2_rn(m0, m1);
-    *reinterpret_cast<__half2*>(oh + C + c) = __floats2half2_rn(d0, d1);
+    *reinterpret_cast<uint32_t*>(oh + c) = pack_half2(m0, m1);
+    *reinterpret_cast<uint32_t*>(oh + C + c) = pack_half2(d0, d1);
   }
 }
 
-// Finishes the column statistics the GEMM write-out accumulated per (m block, window slot)
-// (EpiParams::colsum): window b spans m blocks (b*Tp)/128 .. (b*Tp + Tp - 1)/128; its slot in block m is
-// b - (m*128)/Tp.  mean = k + S/T, var = (Q - S^2/T)/T (shift-invariant), std = sqrt(max(var, 1e-12)).
+// Finishes the column statistics the GEMM write-out accumulated per group of G = gcd(128, Tp) rows
+// (EpiParams::colsum): window b owns the Tp / G groups that start at rows b*Tp + j*G; the group of row r sits
+// at index (r / 128) * (128 / G) + (r % 128) / G.  The groups are added in ascending j, so the result does not
+// depend on which batch slot the window occupies.  mean = k + S/T, var = (Q - S^2/T)/T (shift-invariant),
+// std = sqrt(max(var, 1e-12)).
 // grid (C/256, B), block 256.  std_out / out_h may be null; out_h gets [mean | std] as f16 when std is wanted.
+__device__ __forceinline__ size_t cs_group_index(int b, int j, int Tp, int G) {
+  const int r = b * Tp + j * G;
+  return static_cast<size_t>(r >> 7) * (128 / G) + (r & 127) / G;
+}
+
 __global__ void __launch_bounds__(256)
 colstats_finish_kernel(const float* __restrict__ colsum, const float* __restrict__ colsq,
-                       const float* __restrict__ shift, int C, int Tp, int T, int num_m_blocks,
+                       const float* __restrict__ shift, int C, int Tp, int T, int G,
                        float* __restrict__ mean_out, int ld_out, float* __restrict__ std_out,
                        __half* __restrict__ out_h) {
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
-  const int m_lo = (b * Tp) / 128;
-  const int m_hi = min((b * Tp + Tp - 1) / 128, num_m_blocks - 1);
   float S = 0.f, Q = 0.f;
-  for (int m = m_lo; m <= m_hi; ++m) {
-    const int slot = b - (m * 128) / Tp;
-    const size_t o = (static_cast<size_t>(m) * 2 + slot) * C + c;
+  for (int j = 0; j < Tp / G; ++j) {
+    const size_t o = cs_group_index(b, j, Tp, G) * C + c;
     S += colsum[o];
     if (colsq != nullptr) Q += colsq[o];
   }
@@ -136,122 +140,142 @@ colstats_finish_kernel(const float* __restrict__ colsum, const float* __restrict
     const float sd = sqrtf(fmaxf((Q - S * S * inv) * inv, 1e-12f));
     std_out[static_cast<size_t>(b) * ld_out + c] = sd;
     if (out_h != nullptr) {
-      out_h[static_cast<size_t>(b) * ld_out + c] = __float2half_rn(mean);
-      out_h[static_cast<size_t>(b) * ld_out + C + c] = __float2half_rn(sd);
+      out_h[static_cast<size_t>(b) * ld_out + c] = half_sat(mean);
+      out_h[static_cast<size_t>(b) * ld_out + C + c] = half_sat(sd);
     }
   }
 }
 
-// SE excitation, layer 1: hid[b, j] = relu(W1[j, :] . mean[b, :] + b1[j]).   W1 [S][C] row-major.
-// One CTA = SE_U utterances x 32 hidden units (4 per warp).  (SE_U = 16 and a tcgen05 version of these two
-// layers were measured: neither beats this — both kernels sit at their launch / latency floor.)
-// grid (ceil(B/SE_U), S/32), block 256, dynamic smem SE_U*C floats.
-constexpr int SE_U = 4;
+// The whole squeeze-excitation gate of one SERes2Net block in ONE launch (was: statistics finish, hidden layer
+// and gate as three latency-bound launches, ~59 us per block of which < 10 us was work):
+//   mean[b, c]  = k[c] + (sum of window b's column-sum groups) / T        (or read from `mean_in`)
+//   hid[b, j]   = relu(W1[j, :] . mean[b, :] + b1[j])                      j < 128
+//   scale[b, c] = sigmoid(W2[c, :] . hid[b, :] + b2[c])
+// One CTA = SEG windows; the two weight matrices are f16 ([128][C] each, the second one transposed so that
+// consecutive threads read consecutive channels), 512 KB per CTA out of L2.  speechbrain SEBlock (App. A.2).
+// grid ceil(B / SEG), block 256, static smem.  C = 1024, S = 128 (the only ECAPA configuration).
+constexpr int SEG = 4;
+constexpr int SE_C = 1024;
+constexpr int SE_S = 128;
 __global__ void __launch_bounds__(256)
-se_hidden_kernel(const float* __restrict__ mean, const float* __restrict__ W1,
-                 const float* __restrict__ b1, int B, int C, int S, float* __restrict__ hid) {
+se_gate_kernel(const float* __restrict__ colsum, const float* __restrict__ shift, int Tp, int T, int G,
+               const float* __restrict__ mean_in, const __half* __restrict__ W1h, const float* __restrict__ b1,
+               const __half* __restrict__ W2th, const float* __restrict__ b2, int B,
+               float* __restrict__ mean_out, float* __restrict__ scale) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float sm[];  // [SE_U][C]
-  const int b0 = blockIdx.x * SE_U, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nb = min(SE_U, B - b0);
-  for (int i = tid * 4; i < SE_U * C; i += 256 * 4) {
-    const int u = i / C;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (u < nb) v = *reinterpret_cast<const float4*>(mean + static_cast<size_t>(b0 + u) * C + (i - u * C));
-    *reinterpret_cast<float4*>(sm + i) = v;
+  __shared__ __align__(16) float sm_mean[SEG * SE_C];
+  __shared__ __align__(16) float sm_hid[SEG * SE_S];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b0 = blockIdx.x * SEG;
+  const int nb = min(SEG, B - b0);
+  // ---- squeeze: this thread's 4 channels of every window of the CTA
+  {
+    const int c = tid * 4;
+    float4 kk = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (colsum != nullptr && shift != nullptr) {
+      const float4 sh = *reinterpret_cast<const float4*>(shift + c);
+      kk = make_float4(__half2float(__float2half_rn(sh.x)), __half2float(__float2half_rn(sh.y)),
+                       __half2float(__float2half_rn(sh.z)), __half2float(__float2half_rn(sh.w)));
+    }
+    const float inv = 1.0f / static_cast<float>(T);
+#pragma unroll
+    for (int u = 0; u < SEG; ++u) {
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (u < nb) {
+        if (colsum != nullptr) {
+          float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < Tp / G; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(colsum + cs_group_index(b0 + u, j, Tp, G) * SE_C + c);
+            S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+          }
+          m = make_float4(kk.x + S.x * inv, kk.y + S.y * inv, kk.z + S.z * inv, kk.w + S.w * inv);
+        } else {
+          m = *reinterpret_cast<const float4*>(mean_in + static_cast<size_t>(b0 + u) * SE_C + c);
+        }
+        if (mean_out != nullptr) *reinterpret_cast<float4*>(mean_out + static_cast<size_t>(b0 + u) * SE_C + c) = m;
+      }
+      *reinterpret_cast<float4*>(sm_mean + u * SE_C + c) = m;
+    }
   }
   __syncthreads();
-  // The warp's 4 hidden units together, 4 column steps at a time: 16 independent 128-bit weight loads in
-  // flight per lane (one unit / two steps at a time left the kernel waiting on L2 round trips: 19 us).
-  const int j0 = blockIdx.y * 32 + warp * 4;
-  float acc[4][SE_U];
+  // ---- excitation layer 1: warp w owns hidden units 16w .. 16w+15, four at a time; a lane covers the channel
+  // octets lane, lane+32, lane+64, lane+96 (16 independent 128-bit weight loads in flight)
+  for (int jq = 0; jq < 4; ++jq) {
+    const int j0 = warp * 16 + jq * 4;
+    uint4 wv[4][4];
 #pragma unroll
-  for (int jj = 0; jj < 4; ++jj)
+    for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-    for (int u = 0; u < SE_U; ++u) acc[jj][u] = 0.f;
-  const int n4 = C / 4;
-  for (int i0 = lane; i0 < n4; i0 += 128) {
-    float4 wv[4][4];
+      for (int st = 0; st < 4; ++st)
+        wv[jj][st] = __ldg(reinterpret_cast<const uint4*>(W1h + static_cast<size_t>(j0 + jj) * SE_C) + lane + 32 * st);
+    float acc[4][SEG];
 #pragma unroll
-    for (int s = 0; s < 4; ++s)
+    for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int i = i0 + 32 * s;
-        wv[s][jj] = (i < n4 && j0 + jj < S) ? __ldg(reinterpret_cast<const float4*>(W1 + static_cast<size_t>(j0 + jj) * C) + i)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int u = 0; u < SEG; ++u) acc[jj][u] = 0.f;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int i = i0 + 32 * s;
-      if (i < n4) {
+    for (int st = 0; st < 4; ++st) {
+      const int c8 = (lane + 32 * st) * 8;
 #pragma unroll
-        for (int u = 0; u < SE_U; ++u) {
-          const float4 mv = *reinterpret_cast<const float4*>(sm + u * C + 4 * i);
+      for (int u = 0; u < SEG; ++u) {
+        const float4 m0 = *reinterpret_cast<const float4*>(sm_mean + u * SE_C + c8);
+        const float4 m1 = *reinterpret_cast<const float4*>(sm_mean + u * SE_C + c8 + 4);
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            acc[jj][u] += wv[s][jj].x * mv.x + wv[s][jj].y * mv.y + wv[s][jj].z * mv.z + wv[s][jj].w * mv.w;
+        for (int jj = 0; jj < 4; ++jj) {
+          const __half2* wh = reinterpret_cast<const __half2*>(&wv[jj][st]);
+          const float2 w0 = __half22float2(wh[0]), w1 = __half22float2(wh[1]);
+          const float2 w2 = __half22float2(wh[2]), w3 = __half22float2(wh[3]);
+          float a = acc[jj][u];
+          a = fmaf(w0.x, m0.x, a); a = fmaf(w0.y, m0.y, a); a = fmaf(w1.x, m0.z, a); a = fmaf(w1.y, m0.w, a);
+          a = fmaf(w2.x, m1.x, a); a = fmaf(w2.y, m1.y, a); a = fmaf(w3.x, m1.z, a); a = fmaf(w3.y, m1.w, a);
+          acc[jj][u] = a;
         }
       }
     }
-  }
 #pragma unroll
-  for (int jj = 0; jj < 4; ++jj) {
-    const int j = j0 + jj;
-    if (j >= S) break;
-    const float bj = b1[j];
+    for (int jj = 0; jj < 4; ++jj) {
+      const float bj = __ldg(b1 + j0 + jj);
 #pragma unroll
-    for (int u = 0; u < SE_U; ++u) {
-      const float a = warp_sum(acc[jj][u]);
-      if (lane == 0 && u < nb) hid[static_cast<size_t>(b0 + u) * S + j] = fmaxf(a + bj, 0.f);
-    }
-  }
-}
-
-// SE excitation, layer 2: scale[b, c] = sigmoid(W2[c, :] . hid[b, :] + b2[c]).   W2t [S][C] (transposed
-// conv2 weight, so consecutive threads read consecutive addresses).
-// grid (ceil(B/SE_U), C/256), block 256.  S <= 128, S % 4 == 0.
-__global__ void __launch_bounds__(256)
-se_scale_kernel(const float* __restrict__ hid, const float* __restrict__ W2t,
-                const float* __restrict__ b2, int B, int C, int S, float* __restrict__ scale) {
-  pdl_trigger();
-  pdl_wait();
-  __shared__ __align__(16) float h[SE_U * 128];
-  const int b0 = blockIdx.x * SE_U, tid = threadIdx.x;
-  const int nb = min(SE_U, B - b0);
-  for (int i = tid; i < SE_U * S; i += 256) {
-    const int u = i / S;
-    h[i] = u < nb ? hid[static_cast<size_t>(b0 + u) * S + (i - u * S)] : 0.f;
-  }
-  __syncthreads();
-  const int c = blockIdx.y * 256 + tid;
-  if (c >= C) return;
-  float acc[SE_U];
-  const float bc = b2[c];
-#pragma unroll
-  for (int u = 0; u < SE_U; ++u) acc[u] = bc;
-  // 16 weight rows per step: 16 independent loads in flight per thread (S % 16 == 0 for S = 128)
-  for (int j = 0; j < S; j += 16) {
-    float w[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) w[q] = j + q < S ? __ldg(W2t + static_cast<size_t>(j + q) * C + c) : 0.f;
-#pragma unroll
-    for (int q = 0; q < 16; q += 4) {
-      if (j + q < S) {
-#pragma unroll
-        for (int u = 0; u < SE_U; ++u) {
-          const float4 hv = *reinterpret_cast<const float4*>(h + u * S + j + q);
-          acc[u] = fmaf(hv.x, w[q], acc[u]);
-          acc[u] = fmaf(hv.y, w[q + 1], acc[u]);
-          acc[u] = fmaf(hv.z, w[q + 2], acc[u]);
-          acc[u] = fmaf(hv.w, w[q + 3], acc[u]);
-        }
+      for (int u = 0; u < SEG; ++u) {
+        const float a = warp_sum(acc[jj][u]);
+        if (lane == 0) sm_hid[u * SE_S + j0 + jj] = fmaxf(a + bj, 0.f);
       }
     }
   }
+  __syncthreads();
+  // ---- excitation layer 2 + sigmoid: this thread's 4 channels, 16 weight rows (8 bytes each) in flight
+  {
+    const int c = tid * 4;
+    const float4 bc = *reinterpret_cast<const float4*>(b2 + c);
+    float acc[SEG][4];
 #pragma unroll
-  for (int u = 0; u < SE_U; ++u)
-    if (u < nb) scale[static_cast<size_t>(b0 + u) * C + c] = 1.0f / (1.0f + __expf(-acc[u]));
+    for (int u = 0; u < SEG; ++u) { acc[u][0] = bc.x; acc[u][1] = bc.y; acc[u][2] = bc.z; acc[u][3] = bc.w; }
+    for (int j = 0; j < SE_S; j += 16) {
+      uint2 w[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) w[q] = __ldg(reinterpret_cast<const uint2*>(W2th + static_cast<size_t>(j + q) * SE_C + c));
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float2 wa = __half22float2(*reinterpret_cast<const __half2*>(&w[q].x));
+        const float2 wb = __half22float2(*reinterpret_cast<const __half2*>(&w[q].y));
+#pragma unroll
+        for (int u = 0; u < SEG; ++u) {
+          const float h = sm_hid[u * SE_S + j + q];
+          acc[u][0] = fmaf(h, wa.x, acc[u][0]);
+          acc[u][1] = fmaf(h, wa.y, acc[u][1]);
+          acc[u][2] = fmaf(h, wb.x, acc[u][2]);
+          acc[u][3] = fmaf(h, wb.y, acc[u][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SEG; ++u)
+      if (u < nb)
+        *reinterpret_cast<float4*>(scale + static_cast<size_t>(b0 + u) * SE_C + c) =
+            make_float4(1.0f / (1.0f + __expf(-acc[u][0])), 1.0f / (1.0f + __expf(-acc[u][1])),
+                        1.0f / (1.0f + __expf(-acc[u][2])), 1.0f / (1.0f + __expf(-acc[u][3])));
+  }
 }
 
 // out[r, c] = w[r, c] * scale[b(r), c] + res[r, c]  over ALL rows (halo rows included, so the
@@ -259,9 +283,10 @@ se_scale_kernel(const float* __restrict__ hid, const float* __restrict__ W2t,
 __global__ void __launch_bounds__(256)
 se_apply_kernel(const __half* __restrict__ w, int ld_w, const float* __restrict__ scale,
                 const __half* __restrict__ res, int ld_res, __half* __restrict__ out, int ld_out,
-                long rows, int Tp, int C, int reverse) {
+                long rows, int Tp, int C, int reverse, int* __restrict__ oflow) {
   pdl_trigger();
   pdl_wait();
+  float amax = 0.f;
   const int vec_per_row = C / 8;
   const long total = rows * vec_per_row;
   // from the last row to the first when `reverse`: tdnn2 wrote w in ascending row order, so its last ~100 MB are
@@ -285,10 +310,14 @@ se_apply_kernel(const __half* __restrict__ w, int ld_w, const float* __restrict_
     for (int e = 0; e < 4; ++e) {
       const float2 a = __half22float2(wh[e]);
       const float2 q = __half22float2(rh[e]);
-      oh[e] = __floats2half2_rn(fmaf(a.x, sc[2 * e], q.x), fmaf(a.y, sc[2 * e + 1], q.y));
+      const float o0 = fmaf(a.x, sc[2 * e], q.x), o1 = fmaf(a.y, sc[2 * e + 1], q.y);
+      amax = fmaxf(amax, fmaxf(fabsf(o0), fabsf(o1)));
+      const uint32_t pk = pack_half2(o0, o1);
+      oh[e] = *reinterpret_cast<const __half2*>(&pk);
     }
     *reinterpret_cast<uint4*>(out + r * ld_out + c) = ov;
   }
+  if (amax > kHalfMax && oflow != nullptr) atomicOr(oflow, 1);
 }
 
 // out[i,:] = x[i,:] / (||x[i,:]|| + eps); one warp per row.
@@ -322,9 +351,14 @@ sum_splits_kernel(const float* __restrict__ partial, int n_splits, long stride, 
 // optionally e / (||e|| + eps).  One warp per utterance.
 __global__ void __launch_bounds__(256)
 fc_finish_kernel(const float* __restrict__ partial, int n_splits, long stride, int B, int D,
-                 int l2_normalize, float eps, float* __restrict__ emb) {
+                 int l2_normalize, float eps, float* __restrict__ emb, const int* __restrict__ oflow,
+                 int* __restrict__ oflow_sticky) {
   pdl_trigger();
   pdl_wait();
+  // an activation left the f16 range somewhere in this forward (saturated, so everything stayed finite): the
+  // embeddings would be silently wrong — deliver NaN instead and remember it for the host (SD_ERR_RANGE)
+  const bool poisoned = oflow != nullptr && *oflow != 0;
+  if (poisoned && oflow_sticky != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *oflow_sticky = 1;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -344,7 +378,7 @@ fc_finish_kernel(const float* __restrict__ partial, int n_splits, long stride, i
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int c = lane + 32 * q;
-    if (c < D) emb[static_cast<long>(row) * D + c] = v[q] * inv;
+    if (c < D) emb[static_cast<long>(row) * D + c] = poisoned ? __int_as_float(0x7fc00000) : v[q] * inv;
   }
 }
 

@@ -94,14 +94,14 @@ __device__ __forceinline__ float load_sample(const float* __restrict__ w, int i,
 
 template <int VARIANT>
 __global__ void __launch_bounds__(256, 2)
-fbank_frames_kernel(const float* __restrict__ wav, long wav_stride, int n_samples, int T,
+fbank_frames_kernel(const float* __restrict__ wav, long wav_stride, const long* __restrict__ offsets, int n_samples, int T,
                     const FbankTables* __restrict__ gtab, float* __restrict__ raw) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   FbankSmem& S = *reinterpret_cast<FbankSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * FR_PER_CTA;
-  const float* w = wav + static_cast<long>(b) * wav_stride;
+  const float* w = wav + (offsets != nullptr ? __ldg(offsets + b) : static_cast<long>(b) * wav_stride);
 
   // tables -> shared
   {
@@ -382,7 +382,7 @@ static int get_tables(int variant, FbankTables** out) {
 
 int fbank_launch(const float* wav, long wav_stride, int B, int n_samples, int variant,
                  int mean_norm, float* raw, float* out_f32, __half* out_f16, int Tp, int H,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const long* offsets) {
   if (!wav || !raw || B < 1 || n_samples < NFFT || (variant != 0 && variant != 1))
     return fail(SD_ERR_ARG, "fbank: bad arguments (B=%d n=%d variant=%d)", B, n_samples, variant);
   if (B > 65535) return fail(SD_ERR_ARG, "fbank: B=%d exceeds 65535 windows per call", B);
@@ -401,9 +401,9 @@ int fbank_launch(const float* wav, long wav_stride, int B, int n_samples, int va
   }
   dim3 grid((T + FR_PER_CTA - 1) / FR_PER_CTA, B);
   if (variant == 0)
-    fbank_frames_kernel<0><<<grid, 256, sizeof(FbankSmem), stream>>>(wav, wav_stride, n_samples, T, tab, raw);
+    fbank_frames_kernel<0><<<grid, 256, sizeof(FbankSmem), stream>>>(wav, wav_stride, offsets, n_samples, T, tab, raw);
   else
-    fbank_frames_kernel<1><<<grid, 256, sizeof(FbankSmem), stream>>>(wav, wav_stride, n_samples, T, tab, raw);
+    fbank_frames_kernel<1><<<grid, 256, sizeof(FbankSmem), stream>>>(wav, wav_stride, offsets, n_samples, T, tab, raw);
   SD_CUDA_OK(cudaGetLastError());
   fbank_norm_kernel<<<B, 256, 0, stream>>>(raw, T, variant == 1, mean_norm, out_f32, out_f16, Tp, H);
   SD_CUDA_OK(cudaGetLastError());

@@ -111,12 +111,19 @@ struct EpiParams {
   int C;
   // EPI_AFF
   double* out_f64;  // optional second copy as f64 (AHC working matrix), same ld
-  // EPI_TDNN, n_tile = 256, Tp >= 128, no EF_REFLECT: per-window column statistics fused into the write-out
-  // (tdnn2 -> SE squeeze mean, MFA -> ASP mean/std).  colsum[(m_blk*2 + slot)*N_cols + c] = sum over the
-  // tile's interior frames of window (m_blk*128/Tp + slot) of x - k[c]; colsq the same of (x - k[c])^2;
-  // k[c] = f16(shift[c]), the value a channel takes wherever its ReLU is off.
+  // EPI_TDNN, n_tile = 256, no EF_REFLECT: per-window column statistics fused into the write-out
+  // (tdnn2 -> SE squeeze mean, MFA -> ASP mean/std).  The rows of a tile are cut into groups of
+  // cs_group = gcd(128, Tp) rows; Tp is a multiple of 16, so a group never straddles two windows and always
+  // covers the same window-relative rows.  colsum[(m_blk*(128/cs_group) + g)*N_cols + c] = sum over the interior
+  // frames in group g of x - k[c], added in an order that depends only on the window-relative row; colsq the
+  // same of (x - k[c])^2; k[c] = f16(shift[c]), the value a channel takes wherever its ReLU is off.
   float* colsum;
   float* colsq;
+  // rows per statistics group = gcd(128, Tp) (16 .. 128): window-relative, so a window's partial sums are the
+  // same numbers whichever batch slot (and therefore whichever 128-row tile split) it lands in
+  int cs_group;
+  // overflow flag (device int, may be null): set when an activation exceeded the f16 range and was saturated
+  int* oflow;
 };
 
 struct alignas(64) GemmParams {
@@ -263,6 +270,7 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
   uint8_t* srow = stage_out + rl * 128;
   const int sw = rl & 7;
   uint8_t* sum_stage = stage_out + 32768;  // Res2Net sum tile (n_tile = 128: two 16 KB chunks each)
+  float amax = 0.f;                        // largest |activation| this thread stores (overflow flag)
   for (int c0 = half * 32; c0 < P.n_tile; c0 += 64) {
     uint32_t v[32];
     __syncwarp();
@@ -290,6 +298,9 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
     if (ATT) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(x[j]));
     }
     uint4 pk[4];
 #pragma unroll
@@ -324,7 +335,10 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
         for (int e = 0; e < 4; ++e) {
           float2 fa = __half22float2(ah[e]);
           float2 fy = __half22float2(yh[e]);
-          sh[e] = __floats2half2_rn(fa.x + fy.x, fa.y + fy.y);
+          const float s0 = fa.x + fy.x, s1 = fa.y + fy.y;
+          amax = fmaxf(amax, fmaxf(fabsf(s0), fabsf(s1)));
+          const uint32_t pks = pack_half2(s0, s1);
+          sh[e] = *reinterpret_cast<const __half2*>(&pks);
         }
         sk[q] = *reinterpret_cast<uint4*>(sh);
       }
@@ -335,6 +349,8 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
       }
     }
   }
+  // rows beyond M_rows hold whatever the zero-filled operand rows produced (bias / shift only): finite
+  if (!ATT && amax > kHalfMax && E.oflow != nullptr) atomicOr(E.oflow, 1);
 }
 
 // Write-out of the staged tile by all 256 epilogue threads: 8 lanes cover one 128-byte row chunk,
@@ -397,8 +413,10 @@ __device__ __forceinline__ void tdnn_writeout(const GemmParams& P, int m_blk, in
 
 // Write-out + per-window column statistics for 256-wide tiles (see EpiParams::colsum).  Warp `we` owns the
 // 64-column chunk we>>1 and rows (we&1)*64 .. +63: a store instruction still covers four complete 128-byte
-// lines, and a column's partial sum lives in one warp (shuffle over its 4 row lanes).  The two warps of a
-// chunk combine through `part` (shared memory) in a fixed order, so the result is deterministic.
+// lines, and a column's partial sum lives in one warp (shuffle over its 4 row lanes).  A group of
+// G = cs_group rows is summed as: each lane its rows (every fourth) in ascending order, then the butterfly over
+// the four row lanes, then (G = 128 only) the two warps of a chunk through `part` in a fixed order — an order
+// that depends on the row's position inside its group only, hence not on the window's batch slot.
 template <bool STORE = true>   // STORE = false: statistics only, the tile itself leaves through TMA (EF_TMA_OUT)
 __device__ __forceinline__ void tdnn_writeout_colsum(const GemmParams& P, int m_blk, int n_blk,
                                                      const uint8_t* stage_out, float* part, int et) {
@@ -412,92 +430,88 @@ __device__ __forceinline__ void tdnn_writeout_colsum(const GemmParams& P, int m_
 #pragma unroll
   for (int e = 0; e < 8; ++e)
     k[e] = (E.shift != nullptr && col + e < E.N_cols) ? __half2float(__float2half_rn(__ldg(E.shift + col + e))) : 0.f;
+  const int G = E.cs_group;               // 16, 32, 64 or 128
+  const int GW = G < 64 ? G : 64;         // rows between two flushes of this warp's accumulators
+  const int gpt = BM / G;                 // groups per tile
   const int row0 = m_blk * BM;
-  const int b0 = row0 / E.Tp;
-  const int rb = (b0 + 1) * E.Tp - row0;      // tile-relative first row of window b0 + 1
-  const int tbase0 = row0 - b0 * E.Tp - E.H;  // frame index of tile row 0 inside window b0
-  float s0[8], s1[8], q0[8], q1[8];
+  int p = (row0 + hrow + rlo) % E.Tp;     // window-relative row of this lane's next row
+  float s[8], q[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = q0[e] = q1[e] = 0.f;
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
   __half* out = reinterpret_cast<__half*>(E.out);
   const uint8_t* sbase = stage_out + j * 16384;
-#pragma unroll 4
-  for (int pass = 0; pass < 16; ++pass) {
-    const int rl = hrow + pass * 4 + rlo;
-    const int r = row0 + rl;
-    if (r >= E.M_rows) continue;
-    const uint4 val = *reinterpret_cast<const uint4*>(sbase + rl * 128 + ((sub ^ (rl & 7)) << 4));
-    if (STORE) *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * E.ld_out + E.out_col_off + col) = val;
-    const bool second = rl >= rb;
-    const int t = second ? rl - rb - E.H : rl + tbase0;
-    if (t < 0 || t >= E.T) continue;
-    const __half2* vh = reinterpret_cast<const __half2*>(&val);
-    float d[8];
+  const bool col_ok = col < E.N_cols;
+  for (int quad = 0; quad < 4; ++quad) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(vh[e]);
-      d[2 * e] = f.x - k[2 * e];
-      d[2 * e + 1] = f.y - k[2 * e + 1];
-    }
-    if (!second) {
+    for (int pi = 0; pi < 4; ++pi) {
+      const int rl = hrow + (quad * 4 + pi) * 4 + rlo;
+      const int r = row0 + rl;
+      const int t = p - E.H;
+      p += 4;
+      if (p >= E.Tp) p -= E.Tp;
+      if (r >= E.M_rows) continue;
+      const uint4 val = *reinterpret_cast<const uint4*>(sbase + rl * 128 + ((sub ^ (rl & 7)) << 4));
+      if (STORE) *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * E.ld_out + E.out_col_off + col) = val;
+      if (t < 0 || t >= E.T) continue;
+      const __half2* vh = reinterpret_cast<const __half2*>(&val);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s0[e] += d[e];
-        if (want_sq) q0[e] = fmaf(d[e], d[e], q0[e]);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s1[e] += d[e];
-        if (want_sq) q1[e] = fmaf(d[e], d[e], q1[e]);
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(vh[e]);
+        const float d0 = f.x - k[2 * e], d1 = f.y - k[2 * e + 1];
+        s[2 * e] += d0;
+        s[2 * e + 1] += d1;
+        if (want_sq) {
+          q[2 * e] = fmaf(d0, d0, q[2 * e]);
+          q[2 * e + 1] = fmaf(d1, d1, q[2 * e + 1]);
+        }
       }
     }
-  }
-  // over the 4 row lanes of the warp
+    if (((quad + 1) * 16) % GW != 0) continue;   // warp-uniform: the group (or this warp's half of it) is complete
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 8);
-    s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 16);
-    s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
-    s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
-    if (want_sq) {
-      q0[e] += __shfl_xor_sync(0xffffffffu, q0[e], 8);
-      q0[e] += __shfl_xor_sync(0xffffffffu, q0[e], 16);
-      q1[e] += __shfl_xor_sync(0xffffffffu, q1[e], 8);
-      q1[e] += __shfl_xor_sync(0xffffffffu, q1[e], 16);
+    for (int e = 0; e < 8; ++e) {
+      s[e] += __shfl_xor_sync(0xffffffffu, s[e], 8);
+      s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);
+      if (want_sq) {
+        q[e] += __shfl_xor_sync(0xffffffffu, q[e], 8);
+        q[e] += __shfl_xor_sync(0xffffffffu, q[e], 16);
+      }
+    }
+    if (G < 128) {
+      if (rlo == 0 && col_ok) {
+        const int g = (hrow + quad * 16) / G;
+        float* g0 = E.colsum + (static_cast<size_t>(m_blk) * gpt + g) * E.N_cols + col;
+        *reinterpret_cast<float4*>(g0) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float4*>(g0 + 4) = make_float4(s[4], s[5], s[6], s[7]);
+        if (want_sq) {
+          float* h0 = E.colsq + (static_cast<size_t>(m_blk) * gpt + g) * E.N_cols + col;
+          *reinterpret_cast<float4*>(h0) = make_float4(q[0], q[1], q[2], q[3]);
+          *reinterpret_cast<float4*>(h0 + 4) = make_float4(q[4], q[5], q[6], q[7]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
     }
   }
-  // part: [quantity s|q][chunk j][slot][64 columns]
-  float* ps = part + (j * 2) * 64 + sub * 8;
-  float* pq = ps + 512;
+  if (G < 128) return;
+  // G = 128: the chunk's two warps (rows 0-63, 64-127) combine through shared memory, lower half first
+  float* ps = part + j * 64 + sub * 8;   // part: [quantity s|q][chunk j][64 columns]
+  float* pq = ps + 256;
   if ((we & 1) && rlo == 0) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      ps[e] = s0[e];
-      ps[64 + e] = s1[e];
-      if (want_sq) {
-        pq[e] = q0[e];
-        pq[64 + e] = q1[e];
-      }
+      ps[e] = s[e];
+      if (want_sq) pq[e] = q[e];
     }
   }
   epi_named_barrier();
-  if (!(we & 1) && rlo == 0 && col < E.N_cols) {
-    float* g0 = E.colsum + (static_cast<size_t>(m_blk) * 2) * E.N_cols + col;
-    float* g1 = g0 + E.N_cols;
+  if (!(we & 1) && rlo == 0 && col_ok) {
+    float* g0 = E.colsum + static_cast<size_t>(m_blk) * E.N_cols + col;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      g0[e] = s0[e] + ps[e];
-      g1[e] = s1[e] + ps[64 + e];
-    }
+    for (int e = 0; e < 8; ++e) g0[e] = s[e] + ps[e];
     if (want_sq) {
-      float* h0 = E.colsq + (static_cast<size_t>(m_blk) * 2) * E.N_cols + col;
-      float* h1 = h0 + E.N_cols;
+      float* h0 = E.colsq + static_cast<size_t>(m_blk) * E.N_cols + col;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        h0[e] = q0[e] + pq[e];
-        h1[e] = q1[e] + pq[64 + e];
-      }
+      for (int e = 0; e < 8; ++e) h0[e] = q[e] + pq[e];
     }
   }
 }
@@ -705,8 +719,8 @@ __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, in
       E.pooled[oo] = mean;
       E.pooled[oo + E.C] = sd;
       if (E.pooled_h) {
-        E.pooled_h[oo] = __float2half_rn(mean);
-        E.pooled_h[oo + E.C] = __float2half_rn(sd);
+        E.pooled_h[oo] = half_sat(mean);
+        E.pooled_h[oo + E.C] = half_sat(sd);
       }
     }
   }

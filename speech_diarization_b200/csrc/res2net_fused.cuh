@@ -61,6 +61,9 @@ struct alignas(64) Res2Params {
   uint32_t idesc;                 // M = 128, N = 128, f16
   uint32_t idesc_t1;              // M = 128, N = 32, f16: MODE 3's transposed second tile
   long long* trace;               // debug (SD_R2_TRACE): CTA 0's per-conv clock64 stamps, [conv][18]
+  int* oflow;                     // overflow flag (may be null): a y_i left the f16 range and was saturated.  A sum
+                                  // x_{i+1} + y_i that overflows becomes +-inf in the A buffer; the next convolution's
+                                  // accumulators then carry it into this check
 };
 
 // finer stamps inside the chunks of epilogue warp 4 (quarter 0: two M-tile passes)
@@ -223,6 +226,7 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
     const int t1_end = half == 0 ? 128 + t1_h0 : T;
     const int t1_c = quarter * 32 + lane;
     int n = 0;
+    float amax = 0.f;   // largest |y| this thread produced
     for (int ws = blockIdx.x; ws < P.B; ws += gridDim.x) {
       const int w = P.B - 1 - ws;
       const size_t wrow = static_cast<size_t>(w) * Tp;
@@ -289,7 +293,9 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
           for (int jj = 0; jj < 16; ++jj) {
             const int t = t1_f0 + jj;
             if (t < t1_end) {
-              const __half y = __float2half_rn(fmaf(fmaxf(__uint_as_float(acc[jj]) + cb, 0.f), csc, csh));
+              const float yf = fmaf(fmaxf(__uint_as_float(acc[jj]) + cb, 0.f), csc, csh);
+              amax = fmaxf(amax, fabsf(yf));
+              const __half y = half_sat(yf);
               vcol[static_cast<long>(t) * ld] = y;
               if (t >= T - 1 - H && t <= T - 2) vcol[static_cast<long>(2 * (T - 1) - t) * ld] = y;
               if (has_next) {
@@ -339,6 +345,8 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
               x[4 * e2 + 2] = fmaf(fmaxf(__uint_as_float(acc[o + 2]) + bb.z, 0.f), ss.z, hh.z);
               x[4 * e2 + 3] = fmaf(fmaxf(__uint_as_float(acc[o + 3]) + bb.w, 0.f), ss.w, hh.w);
             }
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(x[0]), fabsf(x[1]))), fmaxf(fmaxf(fabsf(x[2]), fabsf(x[3])),
+                         fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7])))));
             pk[q].x = pack_half2(x[0], x[1]);
             pk[q].y = pack_half2(x[2], x[3]);
             pk[q].z = pack_half2(x[4], x[5]);
@@ -437,6 +445,7 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
+    if (amax > kHalfMax && P.oflow != nullptr) atomicOr(P.oflow, 1);
   }
 
   tc_fence_before();

@@ -297,10 +297,22 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int n, int ab_format
 }
 
 // ------------------------------------------------------------ small helpers
+// Two f32 -> one packed f16x2 (a in the low half), round-to-nearest, SATURATING: a finite value beyond the f16
+// range becomes +-65504 instead of +-inf, so one out-of-range activation (a real checkpoint with a large
+// BatchNorm scale) cannot turn into inf - inf = NaN three layers later.  Saturation is never silent: the
+// epilogues that store activations also raise the plan's overflow flag (EpiParams::oflow), which poisons the
+// embeddings with NaN and makes the host-side call fail with SD_ERR_RANGE.
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // first source -> upper half
+  return r;
 }
+__device__ __forceinline__ __half half_sat(float a) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(a));
+  return __ushort_as_half(r);
+}
+constexpr float kHalfMax = 65504.f;
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

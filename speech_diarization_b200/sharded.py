@@ -72,9 +72,45 @@ def gather_row_blocks(block: torch.Tensor, n_total: int, dst: int = 0, group=Non
     return None
 
 
-def cluster_sharded(emb_all: torch.Tensor, cos_thr: float, group=None, distance_fn=None, ahc_fn=None) -> torch.Tensor:
+class _PhaseTimer:
+    """Per-phase device times of the clustering stage: CUDA events on the current stream when the tensors live
+    on a GPU, perf_counter in the gloo/CPU tests.  `read()` synchronises once, after the last phase."""
+
+    def __init__(self, device: torch.device, enabled: bool):
+        self.cuda = enabled and device.type == "cuda"
+        self.enabled = enabled
+        self.marks: list = []
+        self.names: list[str] = []
+
+    def mark(self, name: str | None = None) -> None:
+        if not self.enabled:
+            return
+        if self.cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append(ev)
+        else:
+            import time
+            self.marks.append(time.perf_counter())
+        if name is not None:
+            self.names.append(name)
+
+    def read(self) -> dict:
+        if not self.enabled or len(self.marks) < 2:
+            return {}
+        if self.cuda:
+            self.marks[-1].synchronize()
+            return {n: self.marks[i].elapsed_time(self.marks[i + 1]) for i, n in enumerate(self.names)}
+        return {n: 1e3 * (self.marks[i + 1] - self.marks[i]) for i, n in enumerate(self.names)}
+
+
+def cluster_sharded(emb_all: torch.Tensor, cos_thr: float, group=None, distance_fn=None, ahc_fn=None,
+                    timings: dict | None = None) -> torch.Tensor:
     """Row-block sharded affinity + AHC on rank 0 + label broadcast.  distance_fn(emb_all, row0, rows)
-    and ahc_fn(dist, threshold) default to the CUDA kernels; the CPU tests inject stand-ins."""
+    and ahc_fn(dist, threshold) default to the CUDA kernels; the CPU tests inject stand-ins.
+    A rank whose shard is empty (n < world * (world - 1) can leave the last ranks without rows) contributes an
+    empty block and still takes part in the gather and the broadcast.  `timings`, when given, receives the
+    milliseconds of each phase on this rank: affinity_rowblock, gather_rowblocks, ahc, broadcast_labels."""
     if distance_fn is None or ahc_fn is None:
         from . import clustering
         distance_fn = distance_fn or clustering.cosine_distance_device
@@ -83,27 +119,58 @@ def cluster_sharded(emb_all: torch.Tensor, cos_thr: float, group=None, distance_
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_range(n, rank, world)
-    block = distance_fn(emb_all, lo, hi - lo)
+    tm = _PhaseTimer(emb_all.device, timings is not None)
+    tm.mark()
+    if hi > lo:
+        block = distance_fn(emb_all, lo, hi - lo)
+    else:
+        block = torch.empty((0, n), dtype=torch.float32, device=emb_all.device)
+    tm.mark("affinity_rowblock")
     full = gather_row_blocks(block, n, 0, group)
+    tm.mark("gather_rowblocks")
     labels = torch.empty((n,), dtype=torch.int32, device=emb_all.device)
     if rank == 0:
         labels.copy_(ahc_fn(full.contiguous(), 1 - cos_thr))
+    del full
+    tm.mark("ahc")
     if world > 1:
         dist.broadcast(labels, src=0, group=group)
+    tm.mark("broadcast_labels")
+    if timings is not None:
+        timings.update(tm.read())
     return labels
 
 
-def embed_windows_sharded(audio: torch.Tensor, win: int, hop: int, encoder, group=None):
-    """audio: the FULL recording as a 1-D f32 tensor on this rank's device (or only this rank's
-    slice plus `offset`, see audio_slice_for).  Returns (all embeddings [N, 192] L2-normalised on every
-    rank, (lo, hi) = this rank's window range)."""
+def embed_windows_sharded(audio: torch.Tensor, win: int, hop: int, encoder, group=None,
+                          n_total_samples: int | None = None, timings: dict | None = None):
+    """Embeds this rank's window range and all-gathers the L2-normalised embeddings.
+
+    audio: 1-D f32 tensor on this rank's device holding EITHER the full recording (n_total_samples None) OR only
+    this rank's slice of it — samples [a0, a1) = audio_slice_for(*shard_range(n, rank, world), win, hop) of a
+    recording of n_total_samples samples ("each rank receives only its audio slice plus a win-hop
+    overlap").  Returns (all embeddings [N, 192] on every rank, (lo, hi) = this rank's window range)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    n = window_count(audio.numel(), win, hop)
+    sliced = n_total_samples is not None
+    n = window_count(int(n_total_samples) if sliced else audio.numel(), win, hop)
     lo, hi = shard_range(n, rank, world)
-    a0, _ = audio_slice_for(lo, hi, win, hop)
-    local = encoder.embed_device(audio[a0:], hop, hi - lo, win, l2_normalize=True)
-    return gather_embeddings(local, n, group), (lo, hi)
+    a0, a1 = audio_slice_for(lo, hi, win, hop)
+    if sliced:
+        if audio.numel() < a1 - a0:
+            raise ValueError(f"rank {rank}: slice of {audio.numel()} samples is shorter than the {a1 - a0} "
+                             f"its windows [{lo}, {hi}) cover")
+        local_audio = audio
+    else:
+        local_audio = audio[a0:]
+    tm = _PhaseTimer(audio.device, timings is not None)
+    tm.mark()
+    local = encoder.embed_device(local_audio, hop, hi - lo, win, l2_normalize=True)
+    tm.mark("embed_shard")
+    out = gather_embeddings(local, n, group)
+    tm.mark("allgather_embeddings")
+    if timings is not None:
+        timings.update(tm.read())
+    return out, (lo, hi)
 
 
 def diarize_windows(audio: torch.Tensor, sr: int, encoder, win_s: float = 1.5, hop_s: float = 0.75,

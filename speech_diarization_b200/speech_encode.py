@@ -123,6 +123,12 @@ class EcapaEncoderB200:
             return out
         if n < 400:
             raise ValueError(f"windows of {n} samples are shorter than one 25 ms analysis frame")
+        if not (torch.is_tensor(audio) and audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous()):
+            raise ValueError("embed_device needs a contiguous f32 CUDA tensor")
+        if audio.device != self.device:
+            raise ValueError(f"audio lives on {audio.device}, the encoder on {self.device}")
+        if wav_stride < 1 or (B - 1) * int(wav_stride) + n > audio.numel():
+            raise ValueError(f"{B} windows of {n} samples every {wav_stride} run past the {audio.numel()}-sample buffer")
         tp = self._tp(1 + n // _HOP)
         if tp > self._max_rows:                      # one window larger than the whole workspace: grow
             self._make_plan(1, n)
@@ -137,6 +143,40 @@ class EcapaEncoderB200:
                                                     out.data_ptr() + 4 * EMB_DIM * b0, st), "sd_ecapa_embed")
         return out
 
+    def embed_offsets_device(self, audio: torch.Tensor, offsets, n_samples: int, l2_normalize: bool = False,
+                             out: torch.Tensor | None = None) -> torch.Tensor:
+        """Embeddings of windows that start at ARBITRARY sample offsets of one CUDA f32 recording: window b =
+        audio[offsets[b] : offsets[b] + n_samples].  offsets: int64 array / tensor.  One launch sequence for all
+        of them (the speech windows of a recording, the sliding windows of all SCD segments).  No host sync."""
+        off = torch.as_tensor(offsets, dtype=torch.int64)
+        B, n = int(off.numel()), int(n_samples)
+        if out is None:
+            out = torch.empty((B, EMB_DIM), dtype=torch.float32, device=self.device)
+        if B == 0:
+            return out
+        if n < 400:
+            raise ValueError(f"windows of {n} samples are shorter than one 25 ms analysis frame")
+        if not (torch.is_tensor(audio) and audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous()
+                and audio.device == self.device):
+            raise ValueError("embed_offsets_device needs a contiguous f32 CUDA tensor on the encoder's device")
+        if not off.is_cuda:
+            if int(off.min()) < 0 or int(off.max()) + n > audio.numel():
+                raise ValueError("a window runs past the audio buffer")
+            off = off.to(self.device)
+        off = off.contiguous()
+        tp = self._tp(1 + n // _HOP)
+        if tp > self._max_rows:
+            self._make_plan(1, n)
+        per_call = max(1, self._max_rows // tp)
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr()
+            for b0 in range(0, B, per_call):
+                nb = min(per_call, B - b0)
+                _lib.check(self._lib.sd_ecapa_embed_offsets(self._plan, audio.data_ptr(), off.data_ptr() + 8 * b0, nb, n,
+                                                            int(bool(l2_normalize)), out.data_ptr() + 4 * EMB_DIM * b0, st),
+                           "sd_ecapa_embed_offsets")
+        return out
+
     def embed_host(self, wavs: np.ndarray, wav_stride: int, n_windows: int, n_samples: int,
                    l2_normalize: bool = False) -> np.ndarray:
         """Embeddings of windows addressed in place in a HOST f32 buffer (numpy, contiguous span): the upload is
@@ -148,6 +188,10 @@ class EcapaEncoderB200:
             return out
         if n < 400:
             raise ValueError(f"windows of {n} samples are shorter than one 25 ms analysis frame")
+        if not (isinstance(wavs, np.ndarray) and wavs.dtype == np.float32 and wavs.flags.c_contiguous):
+            raise ValueError("embed_host needs a C-contiguous float32 numpy array")
+        if wav_stride < 1 or (B - 1) * int(wav_stride) + n > wavs.size:
+            raise ValueError(f"{B} windows of {n} samples every {wav_stride} run past the {wavs.size}-sample buffer")
         tp = self._tp(1 + n // _HOP)
         if tp > self._max_rows:
             self._make_plan(1, n)
@@ -176,6 +220,15 @@ class EcapaEncoderB200:
         x = to_device_f32(wavs, self.device)
         emb = self.embed_device(x, x.stride(0), x.shape[0], x.shape[1])
         return emb.unsqueeze(1)
+
+    def overflowed(self, reset: bool = True) -> bool:
+        """True when a forward since the last reset saturated an activation at the f16 range (its embeddings were
+        delivered as NaN).  Synchronises the current stream."""
+        flag = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sd_ecapa_overflow(self._plan, int(bool(reset)), ctypes.byref(flag), _lib.stream_ptr()),
+                       "sd_ecapa_overflow")
+        return bool(flag.value)
 
     def forward_feats(self, feats: torch.Tensor, l2_normalize: bool = False) -> torch.Tensor:
         """Trunk only, from [B, T, 80] features (parity tests)."""
@@ -232,7 +285,7 @@ def using_ecapa_encoder(device: str | int = "cuda") -> EcapaEncoderB200:
                 "no ECAPA-TDNN weights: call register_ecapa_state_dict(state_dict) or set $SD_ECAPA_CKPT to a "
                 "speechbrain embedding_model.ckpt (the reference fetches LanceaKing/spkrec-ecapa-cnceleb from "
                 "the HF hub, speech_encode.py:66-69; there is no network here)")
-        sd = torch.load(path, map_location="cpu")
+        sd = torch.load(path, map_location="cpu", weights_only=True)
     return EcapaEncoderB200(sd, device=device)
 
 

@@ -40,6 +40,7 @@ def _worker(rank, world, port, n, q):
         assert torch.equal(allx, torch.from_numpy(X))
 
         def distance_fn(emb, row0, rows):
+            assert rows > 0, "an empty shard must not call the distance kernel"
             return torch.from_numpy(co.cosine_distance(emb.numpy())[row0:row0 + rows].copy())
 
         def ahc_fn(d, thr):
@@ -47,7 +48,7 @@ def _worker(rank, world, port, n, q):
 
         labels = sharded.cluster_sharded(allx, 0.68, distance_fn=distance_fn, ahc_fn=ahc_fn)
         ok = co.same_partition(labels.numpy(), lab)
-        block = distance_fn(allx, lo, hi - lo)
+        block = distance_fn(allx, lo, hi - lo) if hi > lo else torch.empty((0, n), dtype=torch.float32)
         full = sharded.gather_row_blocks(block, n, 0)
         if rank == 0:
             ok = ok and np.array_equal(full.numpy(), co.cosine_distance(X))
@@ -58,12 +59,14 @@ def _worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [101, 64])       # odd n: the last shard is shorter and gets padded
-def test_world2_gather_and_cluster(n):
+# odd n: the last shard is shorter and gets padded; n = 5 on 4 ranks: shards of 2, 2, 1 and an EMPTY one (ranks
+# beyond the last shard must still take part in the gather and the broadcast)
+@pytest.mark.parametrize("n,world", [(101, 2), (64, 2), (5, 4)])
+def test_gather_and_cluster(n, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() + n) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
@@ -71,4 +74,4 @@ def test_world2_gather_and_cluster(n):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
-    assert res[0][2] == res[1][2]            # both ranks hold the same labels
+    assert all(r[2] == res[0][2] for r in res)            # every rank holds the same labels

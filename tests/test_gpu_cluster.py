@@ -47,6 +47,17 @@ def test_row_block_sharding_assembles_full_matrix():
     assert torch.equal(f32.double(), f64)
 
 
+def test_empty_row_block_is_not_an_error():
+    """A rank beyond the last shard (n = 9 windows on 8 GPUs) asks for zero rows: an empty block, no SdError
+    (the other ranks would otherwise wait for it in the gather forever)."""
+    X, _ = synth_emb(9, 2, 0.02, 1)
+    xd = torch.from_numpy(X).cuda()
+    assert cl.cosine_distance_device(xd, 9, 0).shape == (0, 9)
+    assert cl.cosine_distance_device(xd, 4, 0).shape == (0, 9)
+    from speech_diarization_b200 import sharded
+    assert [sharded.shard_range(9, r, 8) for r in (4, 5, 7)] == [(8, 9), (9, 9), (9, 9)]
+
+
 def test_anti_stick_cosine_distance_head():
     X, _ = synth_emb(500, 4, 0.05, 2)
     ref = 1 - co.cosine_similarity(co.l2_normalize(X))          # anti_stick_diarize.py:176-177
@@ -104,6 +115,36 @@ def test_ahc_properties_at_n20k():
     perm = np.random.default_rng(1).permutation(20000)
     got_p = cl.cluster_embeddings_device(xd[torch.from_numpy(perm).cuda()].contiguous(), 0.68).cpu().numpy()
     assert co.same_partition(got_p, got[perm])
+
+
+@pytest.mark.parametrize("tag", ["clean", "edge"])
+def test_ahc_n20k_labels_match_reference_golden(tag):
+    """BASELINE config 4 at N = 20 000 against the labels of the reference's own cluster_embeddings (diar_diag.py:213-229;
+    tests/golden/make_golden.py cluster20k): sigma = 0.02 -> 8 clusters, and sigma = 0.045 where the intra-cluster
+    cosine sits near the 0.68 threshold -> 38 clusters."""
+    g = golden("cluster_ref_20k.npz")
+    N, K, seed = (int(v) for v in g[f"{tag}_params"])
+    X, _ = synth_emb(N, K, float(g[f"{tag}_sigma"]), seed)
+    assert abs(float(X.astype(np.float64).sum()) - float(g[f"{tag}_xsum"])) < 1e-6      # same inputs as the golden run
+    got = diar_diag.cluster_embeddings(X, method="agglo", cos_thr=0.68)
+    ref = g[f"{tag}_labels"].astype(np.int64)
+    assert len(set(got.tolist())) == len(set(ref.tolist()))
+    assert co.same_partition(got, ref)
+
+
+def test_ahc_with_exactly_duplicated_rows():
+    """Many exactly duplicated embeddings (silent windows): zero distances and exact f64 ties everywhere.  The
+    reciprocal-nearest-neighbour rounds must still terminate with sklearn's partition."""
+    X, _ = synth_emb(600, 5, 0.03, 17)
+    X[100:300] = X[100]                  # 200 identical rows
+    X[300:340] = X[301]
+    X[500:] = X[[3, 7]].repeat(50, axis=0)
+    for thr in (0.68, 0.9):
+        ref = co.cluster_embeddings(X, "agglo", thr)
+        got = diar_diag.cluster_embeddings(X, "agglo", thr)
+        assert co.same_partition(got, ref), (thr, len(set(ref)), len(set(got)))
+    Y = np.tile(X[:1], (257, 1))         # nothing but duplicates
+    assert len(set(diar_diag.cluster_embeddings(Y, "agglo", 0.68).tolist())) == 1
 
 
 def test_single_sample_raises_like_sklearn():

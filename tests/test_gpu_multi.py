@@ -24,7 +24,14 @@ def _worker(rank, world, port, q):
                                              max_samples=24000)
         y = torch.from_numpy(np.concatenate([synth_wave(1, 16000 * 20, s)[0] for s in (1, 7)])).cuda()
         emb, (lo, hi) = sharded.embed_windows_sharded(y, 24000, 12000, enc)
-        labels = sharded.cluster_sharded(emb, 0.68)
+        # the same from this rank's slice only: samples [a0, a1) of the recording
+        a0, a1 = sharded.audio_slice_for(lo, hi, 24000, 12000)
+        emb_s, rng_s = sharded.embed_windows_sharded(y[a0:a1].clone(), 24000, 12000, enc, n_total_samples=y.numel())
+        assert rng_s == (lo, hi) and torch.equal(emb_s, emb)
+        timings = {}
+        labels = sharded.cluster_sharded(emb, 0.68, timings=timings)
+        assert set(timings) == {"affinity_rowblock", "gather_rowblocks", "ahc", "broadcast_labels"}
+
         segs = sharded.diarize_windows(y, 16000, enc)
         q.put((rank, emb.cpu().numpy(), labels.cpu().numpy(), segs, (lo, hi)))
     finally:
@@ -52,9 +59,9 @@ def test_two_gpu_pipeline_matches_single_gpu():
     n = sharded.window_count(y.numel(), 24000, 12000)
     ref = enc.embed_device(y, 12000, n, 24000, l2_normalize=True).cpu().numpy()
     for rank, emb, labels, segs, rng in res:
-        # same kernels, same inputs; a shard places a window at a different batch offset, which changes the f32
-        # association of the fused SE/ASP time statistics (see test_batch_properties_full_size) -> ~1e-5 on unit-norm embeddings
-        np.testing.assert_allclose(emb, ref, rtol=0, atol=1e-4)
+        # same kernels, same inputs; a shard places a window at a different batch offset, and the forward is
+        # slot-invariant (test_slot_independence_is_bit_exact): bit-identical embeddings
+        np.testing.assert_array_equal(emb, ref)
         assert rng == sharded.shard_range(n, rank, 2)
     np.testing.assert_array_equal(res[0][2], res[1][2])
     single = clustering.cluster_embeddings_device(torch.from_numpy(ref).cuda(), 0.68).cpu().numpy()

@@ -3,6 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from speech_diarization_b200 import clustering
+clustering.ahc_keep_stats(True)
 dev = torch.device("cuda:0")
 def same_partition(a, b):
     fwd, bwd = {}, {}

@@ -3,6 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from speech_diarization_b200 import clustering
+clustering.ahc_keep_stats(True)
 dev = torch.device("cuda:0")
 for N in (int(a) for a in (sys.argv[1:] or ["5000", "20000"])):
     rng = np.random.default_rng(0)
