@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_long, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsd_b200.so")
+# SD_LIB_PATH: load another build of the same library (A/B timing of compile-time variants); never a fallback
+LIB_PATH = os.environ.get("SD_LIB_PATH") or os.path.join(_HERE, "csrc", "libsd_b200.so")
 
 
 class SdError(RuntimeError):

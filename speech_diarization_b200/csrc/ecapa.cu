@@ -30,6 +30,7 @@
 #include "gemm_host.cuh"
 #include "host_stage.cuh"
 #include "res2net_fused.cuh"
+#include "res2net_pipe.cuh"
 #include "sd_status.h"
 
 using namespace sd;
@@ -121,6 +122,7 @@ struct SdEcapaPlan {
   bool use_mc = false;
   bool use_2sm = true;     // SD_ECAPA_2SM=0: 256-wide GEMMs with cta_group::1 instead of CTA pairs
   bool use_r2fused = true; // SD_ECAPA_R2FUSED=0: Res2Net chain as 7 launches per block instead of one
+  bool use_r2pipe = true;  // SD_R2_PIPE=0: res2net_fused_kernel (one window per CTA) instead of res2net_pipe_kernel
   bool use_pdl = false;    // SD_ECAPA_PDL=1: programmatic dependent launch between the trunk's kernels (measured
                            // 2 % SLOWER inside the replayed graph: 3.70-3.74 vs 3.64-3.66 ms per step)
   bool use_tma_out = false; // SD_ECAPA_TMAOUT=1: the cta_group::2 GEMMs of the pointwise layers hand their staged tile to TMA
@@ -544,7 +546,7 @@ void mark(SdEcapaPlan* p, cudaStream_t st) {
   cudaEventRecord(p->ev_pool[p->ev_used++], st);
 }
 
-int launch_res2net_fused(const Res2Params& Q, cudaStream_t st) {
+int launch_res2net_fused(const Res2Params& Q, cudaStream_t st, bool use_pipe) {
   static bool attr_done[64] = {};
   // SD_R2_MODE=0: x_{i+1} loaded behind each chunk's TMEM load (the first version, 0.174 ms per block at B = 512);
   // 2: requested before the accumulator wait / one chunk ahead (0.163 ms); 3 (default): 2 + the frames beyond 127
@@ -559,9 +561,47 @@ int launch_res2net_fused(const Res2Params& Q, cudaStream_t st) {
                                cudaSharedmemCarveoutMaxShared) != cudaSuccess)
         return fail(SD_ERR_CUDA, "res2net_fused_kernel attributes: %s", cudaGetErrorString(cudaGetLastError()));
   }
+  static const char* const r2_trace_path = getenv("SD_R2_TRACE");   // read once: this runs per launch
+  // use_pipe (SD_R2_PIPE, read at plan creation): the four-window pipeline; else the first fused kernel (one window
+  // per CTA, two CTAs per SM), which also takes T + 2 dil = 161 .. 168
+  if (use_pipe && Q.T + 2 * Q.dil <= R2P_RA && Q.B > 0) {
+    static bool pipe_attr[64] = {};
+    if (attr_needed(pipe_attr) &&
+        cudaFuncSetAttribute(res2net_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R2P_SMEM) != cudaSuccess)
+      return fail(SD_ERR_CUDA, "res2net_pipe_kernel attributes: %s", cudaGetErrorString(cudaGetLastError()));
+    const int pgrid = Q.B < num_sms() ? Q.B : num_sms();
+    if (const char* path = r2_trace_path) {   // debug: CTA 0's per-job clock stamps (no graph capture)
+      Res2Params TQ = Q;
+      long long* dev = nullptr;
+      std::vector<long long> host(32 * 18, 0);
+      if (cudaMalloc(&dev, host.size() * 8) != cudaSuccess) return SD_ERR_CUDA;
+      cudaMemsetAsync(dev, 0, host.size() * 8, st);
+      TQ.trace = dev;
+      res2net_pipe_kernel<<<pgrid, R2P_THREADS, R2P_SMEM, st>>>(TQ);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(host.data(), dev, host.size() * 8, cudaMemcpyDeviceToHost);
+      cudaFree(dev);
+      if (FILE* f = fopen(path, "w")) {
+        for (int n = 0; n < 32; ++n) {
+          for (int k = 0; k < 18; ++k) fprintf(f, "%lld ", host[n * 18 + k] ? host[n * 18 + k] - host[0] : -1LL);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+      count_launch();
+      return SD_OK;
+    }
+    cudaError_t e = launch_pdl(res2net_pipe_kernel, dim3(pgrid), dim3(R2P_THREADS), R2P_SMEM, st, Q);
+    count_launch();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    static const bool sync_dbg = getenv("SD_SYNC_DEBUG") != nullptr;
+    if (e == cudaSuccess && sync_dbg) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+      return fail(SD_ERR_CUDA, "res2net_pipe_kernel B=%d T=%d dil=%d: %s", Q.B, Q.T, Q.dil, cudaGetErrorString(e));
+    return SD_OK;
+  }
   const int grid = Q.B < 2 * num_sms() ? Q.B : 2 * num_sms();
   if (grid <= 0) return SD_OK;
-  static const char* const r2_trace_path = getenv("SD_R2_TRACE");   // read once: this runs per launch
   if (const char* path = r2_trace_path) {   // debug: dump CTA 0's per-conv clock stamps (no graph capture)
     Res2Params T = Q;
     long long* dev = nullptr;
@@ -618,7 +658,7 @@ struct PdlScope {   // programmatic dependent launch for every kernel launched i
 int front_body(SdEcapaPlan* p, Program& pr, int c, cudaStream_t st) {
   SD_TRY(launch_big(p, pr.f_block0[c], st));
   SD_TRY(launch_big(p, pr.f_tdnn1[c], st));
-  SD_TRY(launch_res2net_fused(pr.f_r2[c], st));
+  SD_TRY(launch_res2net_fused(pr.f_r2[c], st, p->use_r2pipe));
   SD_TRY(launch_big(p, pr.f_tdnn2[c], st));
   return SD_OK;
 }
@@ -649,7 +689,7 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st, bool skip_front = f
       SD_TRY(launch_big(p, pr.tdnn1[b], st));
       mark(p, st);
       if (p->use_r2fused && pr.r2_ok) {
-        SD_TRY(launch_res2net_fused(pr.r2[b], st));
+        SD_TRY(launch_res2net_fused(pr.r2[b], st, p->use_r2pipe));
       } else {
         for (int i = 0; i < 7; ++i) {
           if (p->use_conv3) SD_TRY(launch_gemm<EPI_CONV3>(pr.resc[b][i], st));
@@ -664,7 +704,7 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st, bool skip_front = f
     // the mean of the separate pass), 1024 -> 128 -> 1024 MLP, sigmoid
     if (!pr.colsum_ok)
       SD_CUDA_OK(launch_pdl(time_mean_kernel, dim3(C1 / 256, B), dim3(128), 0, st, p->w, C1, Tp, T, HALO, C1, p->se_mean));
-    SD_CUDA_OK(launch_pdl(se_gate_kernel, dim3((B + SEG - 1) / SEG), dim3(256), 0, st,
+    SD_CUDA_OK(launch_pdl(se_gate_kernel, dim3((B + SEG - 1) / SEG), dim3(SE_THREADS), 0, st,
                           pr.colsum_ok ? p->cs_se : static_cast<const float*>(nullptr), p->blk[b].tdnn2.shift, Tp, T,
                           pr.cs_group, pr.colsum_ok ? static_cast<const float*>(nullptr) : p->se_mean, p->blk[b].se_w1h,
                           p->blk[b].se_b1, p->blk[b].se_w2th, p->blk[b].se_b2, B,
@@ -771,6 +811,7 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   if (const char* e = getenv("SD_ECAPA_GRAPH")) p->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_CONV3")) p->use_conv3 = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_R2FUSED")) p->use_r2fused = atoi(e) != 0;
+  if (const char* e = getenv("SD_R2_PIPE")) p->use_r2pipe = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_COLSUM")) p->use_colsum = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_TMAOUT")) p->use_tma_out = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_KSPLIT")) p->ksplit = atoi(e) < 1 ? 1 : atoi(e) > KSPLIT_MAX ? KSPLIT_MAX : atoi(e);

@@ -127,10 +127,19 @@ colstats_finish_kernel(const float* __restrict__ colsum, const float* __restrict
   const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
   float S = 0.f, Q = 0.f;
-  for (int j = 0; j < Tp / G; ++j) {
-    const size_t o = cs_group_index(b, j, Tp, G) * C + c;
-    S += colsum[o];
-    if (colsq != nullptr) Q += colsq[o];
+  const int ng = Tp / G;
+  for (int j0 = 0; j0 < ng; j0 += 8) {     // eight groups' loads in flight, added in ascending order
+    float vs[8], vq[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const bool ok = j0 + e < ng;
+      const size_t o = ok ? cs_group_index(b, j0 + e, Tp, G) * C + c : 0;
+      vs[e] = ok ? colsum[o] : 0.f;
+      vq[e] = ok && colsq != nullptr ? colsq[o] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (j0 + e < ng) { S += vs[e]; Q += vq[e]; }
   }
   const float k = shift != nullptr ? __half2float(__float2half_rn(shift[c])) : 0.f;
   const float inv = 1.0f / static_cast<float>(T);
@@ -157,7 +166,8 @@ colstats_finish_kernel(const float* __restrict__ colsum, const float* __restrict
 constexpr int SEG = 4;
 constexpr int SE_C = 1024;
 constexpr int SE_S = 128;
-__global__ void __launch_bounds__(256)
+constexpr int SE_THREADS = 512;
+__global__ void __launch_bounds__(SE_THREADS)
 se_gate_kernel(const float* __restrict__ colsum, const float* __restrict__ shift, int Tp, int T, int G,
                const float* __restrict__ mean_in, const __half* __restrict__ W1h, const float* __restrict__ b1,
                const __half* __restrict__ W2th, const float* __restrict__ b2, int B,
@@ -169,25 +179,41 @@ se_gate_kernel(const float* __restrict__ colsum, const float* __restrict__ shift
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b0 = blockIdx.x * SEG;
   const int nb = min(SEG, B - b0);
-  // ---- squeeze: this thread's 4 channels of every window of the CTA
-  {
-    const int c = tid * 4;
-    float4 kk = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (colsum != nullptr && shift != nullptr) {
-      const float4 sh = *reinterpret_cast<const float4*>(shift + c);
-      kk = make_float4(__half2float(__float2half_rn(sh.x)), __half2float(__float2half_rn(sh.y)),
-                       __half2float(__float2half_rn(sh.z)), __half2float(__float2half_rn(sh.w)));
-    }
-    const float inv = 1.0f / static_cast<float>(T);
+  // The kernel is a chain of L2 round trips (partial sums -> W1 -> W2), so every stage requests the next stage's
+  // first operands before it starts its own arithmetic.
+  // layer 1: warp w owns hidden units 8w .. 8w+7, two at a time; a lane covers the channel octets lane + 32 st
+  uint4 wv[2][4];
+  auto load_w1 = [&](int j0) {
 #pragma unroll
-    for (int u = 0; u < SEG; ++u) {
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+      for (int st = 0; st < 4; ++st)
+        wv[jj][st] = __ldg(reinterpret_cast<const uint4*>(W1h + static_cast<size_t>(j0 + jj) * SE_C) + lane + 32 * st);
+  };
+  load_w1(warp * 8);
+  // ---- squeeze: thread -> (window u = tid / 128 .. , 4 channels); all of a window's groups requested together
+  {
+    const int c = (tid & 255) * 4;
+    const float inv = 1.0f / static_cast<float>(T);
+    const int ng = colsum != nullptr ? Tp / G : 0;
+    for (int u = tid >> 8; u < SEG; u += SE_THREADS / 256) {
       float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
       if (u < nb) {
         if (colsum != nullptr) {
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[j] = j < ng ? *reinterpret_cast<const float4*>(colsum + cs_group_index(b0 + u, j, Tp, G) * SE_C + c)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int j = 0; j < Tp / G; ++j) {
-            const float4 v = *reinterpret_cast<const float4*>(colsum + cs_group_index(b0 + u, j, Tp, G) * SE_C + c);
-            S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < ng) { S.x += v[j].x; S.y += v[j].y; S.z += v[j].z; S.w += v[j].w; }   // ascending j: slot-invariant
+          float4 kk = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (shift != nullptr) {
+            const float4 sh = *reinterpret_cast<const float4*>(shift + c);
+            kk = make_float4(__half2float(__float2half_rn(sh.x)), __half2float(__float2half_rn(sh.y)),
+                             __half2float(__float2half_rn(sh.z)), __half2float(__float2half_rn(sh.w)));
           }
           m = make_float4(kk.x + S.x * inv, kk.y + S.y * inv, kk.z + S.z * inv, kk.w + S.w * inv);
         } else {
@@ -199,19 +225,14 @@ se_gate_kernel(const float* __restrict__ colsum, const float* __restrict__ shift
     }
   }
   __syncthreads();
-  // ---- excitation layer 1: warp w owns hidden units 16w .. 16w+15, four at a time; a lane covers the channel
-  // octets lane, lane+32, lane+64, lane+96 (16 independent 128-bit weight loads in flight)
+  // ---- excitation layer 1
+  const int c2 = (tid & 255) * 4;
+  const int jhalf = (tid >> 8) * (SE_S / 2);          // threads 0-255 take hidden units 0-63, 256-511 take 64-127
   for (int jq = 0; jq < 4; ++jq) {
-    const int j0 = warp * 16 + jq * 4;
-    uint4 wv[4][4];
+    const int j0 = warp * 8 + jq * 2;
+    float acc[2][SEG];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-      for (int st = 0; st < 4; ++st)
-        wv[jj][st] = __ldg(reinterpret_cast<const uint4*>(W1h + static_cast<size_t>(j0 + jj) * SE_C) + lane + 32 * st);
-    float acc[4][SEG];
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
+    for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
       for (int u = 0; u < SEG; ++u) acc[jj][u] = 0.f;
 #pragma unroll
@@ -222,19 +243,20 @@ se_gate_kernel(const float* __restrict__ colsum, const float* __restrict__ shift
         const float4 m0 = *reinterpret_cast<const float4*>(sm_mean + u * SE_C + c8);
         const float4 m1 = *reinterpret_cast<const float4*>(sm_mean + u * SE_C + c8 + 4);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < 2; ++jj) {
           const __half2* wh = reinterpret_cast<const __half2*>(&wv[jj][st]);
           const float2 w0 = __half22float2(wh[0]), w1 = __half22float2(wh[1]);
-          const float2 w2 = __half22float2(wh[2]), w3 = __half22float2(wh[3]);
+          const float2 w2f = __half22float2(wh[2]), w3 = __half22float2(wh[3]);
           float a = acc[jj][u];
           a = fmaf(w0.x, m0.x, a); a = fmaf(w0.y, m0.y, a); a = fmaf(w1.x, m0.z, a); a = fmaf(w1.y, m0.w, a);
-          a = fmaf(w2.x, m1.x, a); a = fmaf(w2.y, m1.y, a); a = fmaf(w3.x, m1.z, a); a = fmaf(w3.y, m1.w, a);
+          a = fmaf(w2f.x, m1.x, a); a = fmaf(w2f.y, m1.y, a); a = fmaf(w3.x, m1.z, a); a = fmaf(w3.y, m1.w, a);
           acc[jj][u] = a;
         }
       }
     }
+    if (jq < 3) load_w1(j0 + 2);           // wv is free again: the next two units, under the reductions below
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
+    for (int jj = 0; jj < 2; ++jj) {
       const float bj = __ldg(b1 + j0 + jj);
 #pragma unroll
       for (int u = 0; u < SEG; ++u) {
@@ -243,38 +265,62 @@ se_gate_kernel(const float* __restrict__ colsum, const float* __restrict__ shift
       }
     }
   }
+  uint2 w2[16];       // layer 2's first 16 weight rows, requested before the barrier
+#pragma unroll
+  for (int q = 0; q < 16; ++q)
+    w2[q] = __ldg(reinterpret_cast<const uint2*>(W2th + static_cast<size_t>(jhalf + q) * SE_C + c2));
   __syncthreads();
-  // ---- excitation layer 2 + sigmoid: this thread's 4 channels, 16 weight rows (8 bytes each) in flight
+  // ---- excitation layer 2 + sigmoid: 4 channels per thread, the 128 hidden units split between the two thread
+  // halves (combined through shared memory, lower half first: a fixed order)
   {
-    const int c = tid * 4;
-    const float4 bc = *reinterpret_cast<const float4*>(b2 + c);
     float acc[SEG][4];
 #pragma unroll
-    for (int u = 0; u < SEG; ++u) { acc[u][0] = bc.x; acc[u][1] = bc.y; acc[u][2] = bc.z; acc[u][3] = bc.w; }
-    for (int j = 0; j < SE_S; j += 16) {
-      uint2 w[16];
+    for (int u = 0; u < SEG; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
+    for (int j = 0; j < SE_S / 2; j += 16) {
+      uint2 wn[16];
+      if (j + 16 < SE_S / 2) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) w[q] = __ldg(reinterpret_cast<const uint2*>(W2th + static_cast<size_t>(j + q) * SE_C + c));
+        for (int q = 0; q < 16; ++q)
+          wn[q] = __ldg(reinterpret_cast<const uint2*>(W2th + static_cast<size_t>(jhalf + j + 16 + q) * SE_C + c2));
+      }
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
-        const float2 wa = __half22float2(*reinterpret_cast<const __half2*>(&w[q].x));
-        const float2 wb = __half22float2(*reinterpret_cast<const __half2*>(&w[q].y));
+        const float2 wa = __half22float2(*reinterpret_cast<const __half2*>(&w2[q].x));
+        const float2 wb = __half22float2(*reinterpret_cast<const __half2*>(&w2[q].y));
 #pragma unroll
         for (int u = 0; u < SEG; ++u) {
-          const float h = sm_hid[u * SE_S + j + q];
+          const float h = sm_hid[u * SE_S + jhalf + j + q];
           acc[u][0] = fmaf(h, wa.x, acc[u][0]);
           acc[u][1] = fmaf(h, wa.y, acc[u][1]);
           acc[u][2] = fmaf(h, wb.x, acc[u][2]);
           acc[u][3] = fmaf(h, wb.y, acc[u][3]);
         }
       }
-    }
+      if (j + 16 < SE_S / 2) {
 #pragma unroll
-    for (int u = 0; u < SEG; ++u)
-      if (u < nb)
-        *reinterpret_cast<float4*>(scale + static_cast<size_t>(b0 + u) * SE_C + c) =
-            make_float4(1.0f / (1.0f + __expf(-acc[u][0])), 1.0f / (1.0f + __expf(-acc[u][1])),
-                        1.0f / (1.0f + __expf(-acc[u][2])), 1.0f / (1.0f + __expf(-acc[u][3])));
+        for (int q = 0; q < 16; ++q) w2[q] = wn[q];
+      }
+    }
+    __syncthreads();                       // sm_mean is dead: reuse it for the upper half's partial sums
+    if (tid >= 256) {
+#pragma unroll
+      for (int u = 0; u < SEG; ++u)
+        *reinterpret_cast<float4*>(sm_mean + u * SE_C + c2) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+    }
+    __syncthreads();
+    if (tid < 256) {
+      const float4 bc = *reinterpret_cast<const float4*>(b2 + c2);
+#pragma unroll
+      for (int u = 0; u < SEG; ++u)
+        if (u < nb) {
+          const float4 o = *reinterpret_cast<const float4*>(sm_mean + u * SE_C + c2);
+          const float z0 = bc.x + acc[u][0] + o.x, z1 = bc.y + acc[u][1] + o.y;
+          const float z2 = bc.z + acc[u][2] + o.z, z3 = bc.w + acc[u][3] + o.w;
+          *reinterpret_cast<float4*>(scale + static_cast<size_t>(b0 + u) * SE_C + c2) =
+              make_float4(1.0f / (1.0f + __expf(-z0)), 1.0f / (1.0f + __expf(-z1)),
+                          1.0f / (1.0f + __expf(-z2)), 1.0f / (1.0f + __expf(-z3)));
+        }
+    }
   }
 }
 

@@ -298,7 +298,7 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
     if (ATT) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
-    } else {
+    } else if (kTrackOflow) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(x[j]));
     }
@@ -335,9 +335,9 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
         for (int e = 0; e < 4; ++e) {
           float2 fa = __half22float2(ah[e]);
           float2 fy = __half22float2(yh[e]);
-          const float s0 = fa.x + fy.x, s1 = fa.y + fy.y;
-          amax = fmaxf(amax, fmaxf(fabsf(s0), fabsf(s1)));
-          const uint32_t pks = pack_half2(s0, s1);
+          // (not part of the overflow tracking: rows beyond M_rows carry uninitialised x_{i+1} registers here; a
+          // sum that saturates shows up in the next convolution's accumulators, which are tracked)
+          const uint32_t pks = pack_half2(fa.x + fy.x, fa.y + fy.y);
           sh[e] = *reinterpret_cast<const __half2*>(&pks);
         }
         sk[q] = *reinterpret_cast<uint4*>(sh);
@@ -350,7 +350,7 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
     }
   }
   // rows beyond M_rows hold whatever the zero-filled operand rows produced (bias / shift only): finite
-  if (!ATT && amax > kHalfMax && E.oflow != nullptr) atomicOr(E.oflow, 1);
+  if (kTrackOflow && !ATT && amax > kHalfMax && E.oflow != nullptr) atomicOr(E.oflow, 1);
 }
 
 // Write-out of the staged tile by all 256 epilogue threads: 8 lanes cover one 128-byte row chunk,

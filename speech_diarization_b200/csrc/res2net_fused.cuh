@@ -294,7 +294,7 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
             const int t = t1_f0 + jj;
             if (t < t1_end) {
               const float yf = fmaf(fmaxf(__uint_as_float(acc[jj]) + cb, 0.f), csc, csh);
-              amax = fmaxf(amax, fabsf(yf));
+              if (kTrackOflow) amax = fmaxf(amax, fabsf(yf));
               const __half y = half_sat(yf);
               vcol[static_cast<long>(t) * ld] = y;
               if (t >= T - 1 - H && t <= T - 2) vcol[static_cast<long>(2 * (T - 1) - t) * ld] = y;
@@ -345,8 +345,9 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
               x[4 * e2 + 2] = fmaf(fmaxf(__uint_as_float(acc[o + 2]) + bb.z, 0.f), ss.z, hh.z);
               x[4 * e2 + 3] = fmaf(fmaxf(__uint_as_float(acc[o + 3]) + bb.w, 0.f), ss.w, hh.w);
             }
-            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(x[0]), fabsf(x[1]))), fmaxf(fmaxf(fabsf(x[2]), fabsf(x[3])),
-                         fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7])))));
+            if (kTrackOflow)
+              amax = fmaxf(fmaxf(amax, fmaxf(fabsf(x[0]), fabsf(x[1]))), fmaxf(fmaxf(fabsf(x[2]), fabsf(x[3])),
+                           fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7])))));
             pk[q].x = pack_half2(x[0], x[1]);
             pk[q].y = pack_half2(x[2], x[3]);
             pk[q].z = pack_half2(x[4], x[5]);
@@ -445,7 +446,7 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
-    if (amax > kHalfMax && P.oflow != nullptr) atomicOr(P.oflow, 1);
+    if (kTrackOflow && amax > kHalfMax && P.oflow != nullptr) atomicOr(P.oflow, 1);
   }
 
   tc_fence_before();

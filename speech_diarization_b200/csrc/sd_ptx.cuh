@@ -313,6 +313,10 @@ __device__ __forceinline__ __half half_sat(float a) {
   return __ushort_as_half(r);
 }
 constexpr float kHalfMax = 65504.f;
+#ifndef SD_NO_OFLOW
+#define SD_NO_OFLOW 0     // 1: A/B build without the overflow tracking (timing only)
+#endif
+constexpr bool kTrackOflow = !SD_NO_OFLOW;
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -121,14 +121,26 @@ def test_ahc_properties_at_n20k():
 def test_ahc_n20k_labels_match_reference_golden(tag):
     """BASELINE config 4 at N = 20 000 against the labels of the reference's own cluster_embeddings (diar_diag.py:213-229;
     tests/golden/make_golden.py cluster20k): sigma = 0.02 -> 8 clusters, and sigma = 0.045 where the intra-cluster
-    cosine sits near the 0.68 threshold -> 38 clusters."""
+    cosine sits near the 0.68 threshold -> 38 clusters.
+
+    "clean" runs the whole device path (affinity kernel + AHC kernel).  "edge" feeds the AHC kernel the oracle's own
+    distance matrix: that data set has near-tied sub-clusters just under the cut, and which of them pairs up first
+    flips with perturbations of the distances far inside the 1e-5 affinity gate (measured: the device affinity is
+    within 1.6e-6 of sklearn's everywhere, yet scipy itself run on it finds 39 clusters, its last merge moving from
+    2.0e-5 below the threshold to 2.0e-5 above).  So at this tolerance only the clustering kernel can be held to the
+    reference's labels there, and it is: same matrix in, same partition out."""
     g = golden("cluster_ref_20k.npz")
     N, K, seed = (int(v) for v in g[f"{tag}_params"])
     X, _ = synth_emb(N, K, float(g[f"{tag}_sigma"]), seed)
     assert abs(float(X.astype(np.float64).sum()) - float(g[f"{tag}_xsum"])) < 1e-6      # same inputs as the golden run
-    got = diar_diag.cluster_embeddings(X, method="agglo", cos_thr=0.68)
     ref = g[f"{tag}_labels"].astype(np.int64)
-    assert len(set(got.tolist())) == len(set(ref.tolist()))
+    if tag == "clean":
+        got = diar_diag.cluster_embeddings(X, method="agglo", cos_thr=0.68)
+    else:
+        D = torch.from_numpy(co.cosine_distance(X)).cuda()
+        assert float((cl.cosine_distance_device(torch.from_numpy(X).cuda()) - D).abs().max()) <= AFF_TOL
+        got = cl.ahc_average_device(D, 1 - 0.68)[0].cpu().numpy()
+    assert len(set(got.tolist())) == len(set(ref.tolist())) == (8 if tag == "clean" else 38)
     assert co.same_partition(got, ref)
 
 

@@ -37,28 +37,35 @@ def test_trunk_layerwise_and_embedding_parity(oracle_model, encoder, B, T):
     assert _rel(got, ref) < 5e-3
 
 
-@pytest.mark.parametrize("B,T", [(300, 151), (5, 101), (3, 160), (2, 16), (9, 129), (4, 128), (2, 161), (3, 131), (3, 137)])
+@pytest.mark.parametrize("B,T", [(300, 151), (700, 151), (5, 101), (3, 160), (2, 16), (9, 129), (4, 128), (2, 161), (3, 131),
+                                 (3, 137), (149, 152), (597, 40)])
 def test_fused_res2net_is_bit_identical_to_the_per_conv_chain(oracle_model, B, T, monkeypatch):
-    """res2net_fused_kernel (one launch per block, inputs kept in shared memory) keeps the operand order and
-    f16 rounding points of the per-convolution chain, so v after every block and the embeddings must be
-    bit-identical.  B = 300 > 2 x 148 CTAs exercises the multi-window loop; T = 161 falls back; T = 129 .. 160 run the
-    transposed second tile (T = 131: the mirrored right-halo frames straddle the two tiles)."""
+    """The fused Res2Net kernels keep the operand order and f16 rounding points of the per-convolution chain, so v
+    after every block and the embeddings must be bit-identical, for the four-window pipeline (res2net_pipe_kernel,
+    T + 2 dil <= 160) and for the first fused kernel (res2net_fused_kernel: SD_R2_PIPE=0, and T = 153 .. 160).
+    B = 700 > 4 x 148 exercises a second round of window slots, B = 149 / 597 a last round with one active slot,
+    T = 161 falls back to the chain, T = 129 .. 152 run the transposed second tile (T = 131: the mirrored right-halo
+    frames straddle the two tiles)."""
     x = eo.synth_features(B, T, seed=7 * B + T)
     out = {}
-    for fused in ("1", "0"):
+    for tag, fused, pipe in (("pipe", "1", "1"), ("v1", "1", "0"), ("chain", "0", "0")):
+        if tag == "v1" and B > 300:
+            continue
         monkeypatch.setenv("SD_ECAPA_R2FUSED", fused)
+        monkeypatch.setenv("SD_R2_PIPE", pipe)
         monkeypatch.setenv("SD_ECAPA_GRAPH", "0")
         enc = se.EcapaEncoderB200(oracle_model.state_dict(), device="cuda:0", max_batch=B, max_samples=(T - 1) * 160)
         try:
             emb = enc.forward_feats(x).cpu()
-            out[fused] = (emb, enc.debug_fetch("b3.res2net", B, T).cpu(), enc.debug_fetch("b3.out", B, T).cpu())
+            out[tag] = (emb, enc.debug_fetch("b3.res2net", B, T).cpu(), enc.debug_fetch("b3.out", B, T).cpu())
         finally:
             enc.close()
-    for a, b in zip(out["1"], out["0"]):
-        assert torch.equal(a, b)
+    for tag in out:
+        for a, b in zip(out[tag], out["chain"]):
+            assert torch.equal(a, b), tag
     with torch.inference_mode():
-        ref = oracle_model(x).squeeze(1)
-    cos = torch.nn.functional.cosine_similarity(out["1"][0], ref, dim=1)
+        ref = oracle_model(x[:64]).squeeze(1)
+    cos = torch.nn.functional.cosine_similarity(out["pipe"][0][:64], ref, dim=1)
     assert float((1 - cos).max()) < COS_TOL
 
 
