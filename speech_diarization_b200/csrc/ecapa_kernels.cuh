@@ -200,15 +200,17 @@ se_gate_kernel(const float* __restrict__ colsum, const float* __restrict__ shift
       float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
       if (u < nb) {
         if (colsum != nullptr) {
-          float4 v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            v[j] = j < ng ? *reinterpret_cast<const float4*>(colsum + cs_group_index(b0 + u, j, Tp, G) * SE_C + c)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j0 = 0; j0 < ng; j0 += 8) {     // eight groups' loads in flight (a 1.5 s window has five)
+            float4 v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < ng) { S.x += v[j].x; S.y += v[j].y; S.z += v[j].z; S.w += v[j].w; }   // ascending j: slot-invariant
+            for (int j = 0; j < 8; ++j)
+              v[j] = j0 + j < ng ? *reinterpret_cast<const float4*>(colsum + cs_group_index(b0 + u, j0 + j, Tp, G) * SE_C + c)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j0 + j < ng) { S.x += v[j].x; S.y += v[j].y; S.z += v[j].z; S.w += v[j].w; }   // ascending: slot-invariant
+          }
           float4 kk = make_float4(0.f, 0.f, 0.f, 0.f);
           if (shift != nullptr) {
             const float4 sh = *reinterpret_cast<const float4*>(shift + c);

@@ -17,4 +17,4 @@ torch.cuda.synchronize()
 rows = [[int(v) for v in l.split()] for l in open("gpurun_out/r2p_trace.txt")]
 print("job  mma_start mma_issued | w0: wait t_full tail chunk0 arrive end | w7: wait t_full tail chunk0 arrive end")
 for n, r in enumerate(rows[:32]):
-    print(f"{n:3d} {r[0]:8d} {r[1]:8d} | " + " ".join(f"{v:7d}" for v in r[2:8]) + " | " + " ".join(f"{v:7d}" for v in r[8:14]))
+    print(f"{n:3d} {r[0]:8d} {r[1]:8d} | " + " ".join(f"{v:7d}" for v in r[2:9]) + " | " + " ".join(f"{v:7d}" for v in r[9:16]))
