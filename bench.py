@@ -409,13 +409,18 @@ def cluster_leg(device, rank: int, world: int) -> dict:
         torch.cuda.synchronize()
         t["allgather_embeddings"] = ev[0].elapsed_time(ev[1])
         t["total"] = ev[0].elapsed_time(ev[2])
+        # phases as rank 0 sees them (it runs the AHC; the other ranks spend that time waiting in the label
+        # broadcast), total = max over ranks
         names = sorted(t)
         v = torch.tensor([t[k] for k in names], device=device)
-        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([t["total"]], device=device)
+        dist.broadcast(v, src=0)
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         t = dict(zip(names, [float(x) for x in v.tolist()]))
-        if rep and (best is None or t["total"] < best["total"]):      # rep 0 = warm-up (allocations, NCCL channels)
+        t["total_max_over_ranks"] = float(tot.item())
+        if rep and (best is None or t["total_max_over_ranks"] < best["total_max_over_ranks"]):   # rep 0 = warm-up
             best = t
-    out = {"n": N, "world": world, "phase_ms_max_over_ranks": best,
+    out = {"n": N, "world": world, "phase_ms_rank0": best,
            "gather_bytes": {"embeddings": N * 192 * 4, "row_blocks_to_rank0": int(4 * N * N * (world - 1) / world)}}
     if rank == 0:
         single = clustering.cluster_embeddings_device(emb_all, 0.68)

@@ -51,6 +51,7 @@ static_assert(2 * (R2_SMEM + 1024) <= 233472, "two CTAs per SM");
 struct alignas(64) Res2Params {
   CUtensorMap tmapU;              // u [rows, ld] f16, box = 64 channels x (T + 2*dil) rows
   CUtensorMap tmapW[R2_CONVS];    // conv i weights [128 out, 3 taps * 128 in] f16, box = 64 x 128
+  CUtensorMap tmapWh[R2_CONVS];   // the same tensor, box = 64 x 64: half a weight box (2-CTA multicast, res2net_pipe.cuh)
   const float* bias[R2_CONVS];
   const float* scale[R2_CONVS];
   const float* shift[R2_CONVS];

@@ -25,7 +25,13 @@
 //     transposed in registers (three xor-shuffle stages) so that x_{i+1} arrives and y_i / x_{i+1} + y_i leave as
 //     16-byte pieces, 64 contiguous bytes per frame per four lanes — no staging tile, no 2-byte stores (sixteen
 //     STS.U16 + sixteen STG.U16 per thread cost ~5.5 k of the first version's ~10 k-cycle epilogue).
-// Weights stream through a 4-slot TMA ring (L2-resident, 96 KB per convolution).
+// Weights stream through a 4-slot TMA ring (L2-resident, 96 KB per convolution).  MC = true (default): the kernel runs
+// on 2-CTA clusters and every weight box is fetched ONCE per pair — each CTA loads the half of the box its rank owns
+// and multicasts it into both CTAs' ring slots.  With every SM streaming 96 KB of weights per job the launch sat at
+// the L2 bandwidth cap (~4.3 KB/clk of weights alone, SD_R2P_DBG probes: without any x / y traffic a job was still
+// bound by weight delivery, 550 cycles per 16 KB box against 320 of tensor work), and all other global accesses
+// queued behind them.  The two CTAs walk the same sequence of weight boxes: a CTA with one window less than its
+// partner consumes (and releases) the boxes of the missing job without issuing MMAs.
 //
 // The products, their order inside every accumulator and the f16 rounding points are those of the per-convolution
 // path, so v is bit-identical to it (tests/test_gpu_ecapa.py).
@@ -39,6 +45,9 @@
 
 #ifndef SD_R2P_DBG
 #define SD_R2P_DBG 0     // timing probes (wrong results): 1 no global stores of y, 2 no loads of x_{i+1}, 4 no input-buffer stores
+#endif
+#ifndef SD_R2P_L2PF
+#define SD_R2P_L2PF 1    // L2 prefetch of the next convolution's x sub-band at the end of every epilogue
 #endif
 #ifndef SD_R2P_TRACE
 #define SD_R2P_TRACE 0   // 1: compile the clock-stamp trace in (Res2Params::trace, tools/r2p_trace.py); costs registers
@@ -63,6 +72,7 @@ static_assert(R2P_SMEM <= 232448, "exceeds the 227 KB of shared memory a CTA can
 // 18 warps land 5 + 5 + 4 + 4 on the four sub-partitions (16 384 registers each), so a thread can have at most
 // 16384 / (5 * 32) = 102 -> 96 registers.  The epilogue is written to stay under that: with 222 KB of shared memory
 // carved out there is hardly any L1 left, and every spilled access would be an L2 round trip.
+template <bool MC>
 __global__ void __launch_bounds__(R2P_THREADS, 1)
 res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -86,12 +96,16 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
   const int G = gridDim.x;
   const int n_mine = (P.B - static_cast<int>(blockIdx.x) + G - 1) / G;   // windows blockIdx.x, + G, ...
   const int rounds = (n_mine + R2P_SLOTS - 1) / R2P_SLOTS;
+  // the weight-box sequence is the pair's: that of its even CTA, which never has fewer windows than the odd one
+  const int crank = MC ? static_cast<int>(cluster_ctarank()) : 0;
+  const int n_pair = MC ? (P.B - (static_cast<int>(blockIdx.x) & ~1) + G - 1) / G : n_mine;
+  const int rounds_w = (n_pair + R2P_SLOTS - 1) / R2P_SLOTS;
 
   if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < R2P_WSLOTS; ++s) {
         mbar_init(&w_full[s], 1);
-        mbar_init(&w_empty[s], 1);
+        mbar_init(&w_empty[s], MC ? 2 : 1);     // MC: both CTAs of the pair must release a slot
       }
       for (int s = 0; s < R2P_SLOTS; ++s) {
         mbar_init(&a_full[s], 1);
@@ -110,6 +124,7 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
@@ -121,11 +136,12 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       tma_prefetch_desc(&P.tmapU);
-      for (int i = 0; i < R2_CONVS; ++i) tma_prefetch_desc(&P.tmapW[i]);
+      for (int i = 0; i < R2_CONVS; ++i) tma_prefetch_desc(MC ? &P.tmapWh[i] : &P.tmapW[i]);
       int slot = 0;
       uint32_t ph = 0;
-      for (int r = 0; r < rounds; ++r) {
-        const int nact = min(R2P_SLOTS, n_mine - r * R2P_SLOTS);
+      for (int r = 0; r < rounds_w; ++r) {
+        const int nact = max(0, min(R2P_SLOTS, n_mine - r * R2P_SLOTS));
+        const int nact_w = min(R2P_SLOTS, n_pair - r * R2P_SLOTS);
         for (int s = 0; s < nact; ++s) {
           if (r > 0) mbar_wait(&a_free[s], (r - 1) & 1);   // the previous window's last convolution is done reading
           mbar_arrive_expect_tx(&a_full[s], static_cast<uint32_t>(2 * RA * 128));
@@ -134,12 +150,16 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
           tma_load_2d(abuf + s * R2P_A_BYTES + R2P_A_CHUNK, &P.tmapU, &a_full[s], R2_SUB + 64, row0);
         }
         for (int i = 0; i < R2_CONVS; ++i)
-          for (int s = 0; s < nact; ++s)
+          for (int s = 0; s < nact_w; ++s)
             for (int kc = 0; kc < 2; ++kc)
               for (int j = 0; j < 3; ++j) {
                 mbar_wait(&w_empty[slot], ph ^ 1);
-                mbar_arrive_expect_tx(&w_full[slot], R2_WBOX);
-                tma_load_2d(wring + slot * R2_WBOX, &P.tmapW[i], &w_full[slot], j * R2_SUB + kc * 64, 0);
+                mbar_arrive_expect_tx(&w_full[slot], R2_WBOX);   // the whole box: this CTA's half + the peer's
+                if (MC)
+                  tma_load_2d_mc(wring + slot * R2_WBOX + crank * (R2_WBOX / 2), &P.tmapWh[i], &w_full[slot],
+                                 j * R2_SUB + kc * 64, crank * 64, 0x3);
+                else
+                  tma_load_2d(wring + slot * R2_WBOX, &P.tmapW[i], &w_full[slot], j * R2_SUB + kc * 64, 0);
                 if (++slot == R2P_WSLOTS) { slot = 0; ph ^= 1; }
               }
       }
@@ -153,10 +173,20 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
       uint32_t ready_ph = 0, empty_ph = 0;   // phase bits: bit s of a_ready[s], bit a of t_empty[a]
       int acc = 0;
       const uint32_t idesc = make_idesc_f16(((T + 15) >> 4) << 4, 0);   // M = 128 channels, N = frames
-      for (int r = 0; r < rounds; ++r) {
-        const int nact = min(R2P_SLOTS, n_mine - r * R2P_SLOTS);
+      for (int r = 0; r < rounds_w; ++r) {
+        const int nact = max(0, min(R2P_SLOTS, n_mine - r * R2P_SLOTS));
+        const int nact_w = min(R2P_SLOTS, n_pair - r * R2P_SLOTS);
         for (int i = 0; i < R2_CONVS; ++i)
-          for (int s = 0; s < nact; ++s, ++job) {
+          for (int s = 0; s < nact_w; ++s) {
+            if (s >= nact) {
+              // the partner's job without a counterpart here: consume and release its weight boxes
+              for (int b = 0; b < 6; ++b) {
+                mbar_wait(&w_full[slot], ph);
+                umma_commit_mc(&w_empty[slot], 0x3);
+                if (++slot == R2P_WSLOTS) { slot = 0; ph ^= 1; }
+              }
+              continue;
+            }
             if (i == 0) mbar_wait(&a_full[s], r & 1);
             else { mbar_wait(&a_ready[s], (ready_ph >> s) & 1u); ready_ph ^= 1u << s; }
             if (job >= R2P_ACCS) { mbar_wait(&t_empty[acc], (empty_ph >> acc) & 1u); empty_ph ^= 1u << acc; }
@@ -174,13 +204,15 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                   umma_f16(d0, dw + 2 * kk, dx + 2 * kk, idesc, (kc | j | kk) ? 1u : 0u);
-                umma_commit(&w_empty[slot]);
+                if (MC) umma_commit_mc(&w_empty[slot], 0x3);   // the slot is free once BOTH CTAs' MMAs have read it
+                else umma_commit(&w_empty[slot]);
                 if (++slot == R2P_WSLOTS) { slot = 0; ph ^= 1; }
               }
             umma_commit(&t_full[acc]);
             if (i == R2_CONVS - 1) umma_commit(&a_free[s]);
             if (SD_R2P_TRACE && P.trace != nullptr && blockIdx.x == 0 && job < 32) P.trace[job * 18 + 1] = clock64();
             if (++acc == R2P_ACCS) acc = 0;
+            ++job;
           }
       }
     }
@@ -314,6 +346,13 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
             if (has_next) mbar_arrive(&a_ready[s]);
           }
           if (trc) tp[3] = clock64();
+          // pull the x sub-band the window's NEXT convolution will add (sub-band i + 3) from HBM into L2 now, four
+          // jobs ahead of its use: the loads above then pay an L2 hit instead of a DRAM round trip
+          if (SD_R2P_L2PF && i + 3 < 8) {
+            const __half* const xp = P.u + (i + 3) * R2_SUB + (wrow + H) * ld;
+            for (int idx = gw * 32 + lane; idx < 2 * T; idx += 256)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + static_cast<size_t>(idx >> 1) * ld + (idx & 1) * 64));
+          }
         }
     }
     if (kTrackOflow && amax > kHalfMax && P.oflow != nullptr) atomicOr(P.oflow, 1);
@@ -321,6 +360,7 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();   // the peer may still multicast into this CTA's ring / arrive on its barriers
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
