@@ -432,6 +432,64 @@ def cluster_leg(device, rank: int, world: int) -> dict:
     return out
 
 
+def corpus_leg(enc, device, rank: int, world: int) -> dict:
+    """BASELINE config 3 END TO END on N > 1 GPUs: an 8 h synthetic multi-speaker corpus (38 399 windows of 1.5 s /
+    0.75 s), each rank holding ONLY its audio slice (+ the win - hop overlap, sharded.audio_slice_for) in host
+    memory: upload of the slice -> fbank + ECAPA on the rank's windows -> one NCCL all-gather of the L2-normalised
+    embeddings -> row-block affinity -> gather of the row blocks -> AHC on rank 0 -> label broadcast.  Device time per
+    phase (rank 0) and total (max over ranks, from the start of the upload to the labels)."""
+    import torch.distributed as dist
+    from speech_diarization_b200 import sharded
+    hours = 8
+    n_total = hours * 3600 * SR
+    n_win = sharded.window_count(n_total, WIN, HOP)
+    lo, hi = sharded.shard_range(n_win, rank, world)
+    a0, a1 = sharded.audio_slice_for(lo, hi, WIN, HOP)
+    # the rank's slice of the corpus: generated per hour (seeded by the hour index, so every world size sees the
+    # same recording), cut to [a0, a1)
+    parts = []
+    for h in range(a0 // (3600 * SR), (a1 - 1) // (3600 * SR) + 1):
+        seg = synth_audio(3600, 8, seed=100 + h, device=device)
+        s0, s1 = max(a0, h * 3600 * SR) - h * 3600 * SR, min(a1, (h + 1) * 3600 * SR) - h * 3600 * SR
+        parts.append(seg[s0:s1].cpu())
+        del seg
+    host = torch.cat(parts).pin_memory()
+    del parts
+    torch.cuda.empty_cache()
+    best = None
+    for rep in range(2):
+        dist.barrier(); torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_emb, t_cl = {}, {}
+        ev[0].record()
+        slice_dev = host.to(device, non_blocking=True)
+        ev[1].record()
+        emb, rng = sharded.embed_windows_sharded(slice_dev, WIN, HOP, enc, n_total_samples=n_total, timings=t_emb)
+        labels = sharded.cluster_sharded(emb, 0.68, timings=t_cl)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t = {"upload_slice": ev[0].elapsed_time(ev[1]), **t_emb, **t_cl}
+        names = sorted(t)
+        v = torch.tensor([t[k] for k in names], device=device)
+        tot = torch.tensor([ev[0].elapsed_time(ev[2])], device=device)
+        dist.broadcast(v, src=0)
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        t = dict(zip(names, [float(x) for x in v.tolist()]))
+        t["total_max_over_ranks"] = float(tot.item())
+        if rep:
+            best = t
+        del slice_dev
+    lab = labels.to(torch.int64)
+    chk = torch.stack([lab.sum(), (lab * torch.arange(lab.numel(), device=device)).sum()])
+    lo_chk, hi_chk = chk.clone(), chk.clone()
+    dist.all_reduce(lo_chk, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_chk, op=dist.ReduceOp.MAX)
+    return {"audio_hours": hours, "windows": int(n_win), "windows_this_rank": int(hi - lo), "world": world,
+            "phase_ms_rank0": best, "rtf": best["total_max_over_ranks"] * 1e-3 / (hours * 3600),
+            "clusters": int(labels.max().item()) + 1, "labels_identical_on_all_ranks": bool(torch.equal(lo_chk, hi_chk)),
+            "note": "random-init ECAPA weights: the partition is not a speaker partition; the leg measures the pipeline"}
+
+
 def post_leg(device, with_cpu: bool) -> dict:
     """SURVEY §8f rank 4 at the sizes of BASELINE configs 4 / 5: AS-norm of N = 20 000 segment embeddings against
     themselves (diar_diag.py:389), Viterbi over the 35 990 windows of the dense pass at the reference's 0.1 s step
@@ -519,8 +577,34 @@ def dense_pass_leg(enc, audio, device) -> dict:
         torch.cuda.synchronize()
         if rep:
             best_ms = min(best_ms, ev0.elapsed_time(ev1))
-    return {"windows": int(n), "window_s": 1.0, "hop_s": 0.5, "ms": best_ms,
-            "rtf": best_ms * 1e-3 / (audio.numel() / SR), "embeddings_per_s": n / (best_ms * 1e-3)}
+    out = {"windows": int(n), "window_s": 1.0, "hop_s": 0.5, "ms": best_ms,
+           "rtf": best_ms * 1e-3 / (audio.numel() / SR), "embeddings_per_s": n / (best_ms * 1e-3)}
+    # The same pass END TO END through the reference-facing call (anti_stick_diarize.reassign_windows, the body of
+    # frame_reassign :411-460): host numpy audio in, Segment list out — upload of the 230 MB recording, VAD gating of
+    # the windows (speech mask = the synthetic turns), embedding from one offset list, centroid arg-max, run-length
+    # encoding and neighbour merge on the device, the (small) segment table back.  Wall clock, incl. every sync.
+    try:
+        from speech_diarization_b200 import anti_stick_diarize as asd, speech_encode
+        from speech_diarization_b200.weights import random_ecapa_state_dict
+        speech_encode.register_ecapa_state_dict(random_ecapa_state_dict(0))
+        y = audio.cpu().numpy()
+        # speech mask: 4 s of speech, 0.5 s pause, repeated (what a VAD hands the pass)
+        mask = [asd.Segment(t0, min(t0 + 4.0, len(y) / SR)) for t0 in np.arange(0.0, len(y) / SR, 4.5)]
+        cm = cents.cpu().numpy()
+        best_s, segs = 1e9, []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            segs = asd.reassign_windows(y, SR, mask, np.arange(4), cm, smooth_step=0.5, win=1.0)
+            dt = time.perf_counter() - t0
+            if rep:
+                best_s = min(best_s, dt)
+        out["e2e"] = {"api": "anti_stick_diarize.reassign_windows(host audio, speech mask, centroids) -> Segment list",
+                      "ms": 1e3 * best_s, "rtf": best_s / (len(y) / SR), "segments": len(segs),
+                      "h2d_bytes": int(y.nbytes),
+                      "speech_windows": int(asd._get_speech_windows(y, SR, mask, win, hop)[1].size)}
+    except Exception as e:      # reported, not fatal to the bench line
+        out["e2e"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
 
 
 PEAK_HBM = 6450.9
@@ -752,15 +836,23 @@ def main() -> None:
             line["dense_pass"] = dense_pass_leg(enc, audio, device)
             line["ahc"] = ahc_leg(device, with_cpu=not args.no_cpu_baseline)
             line["post"] = post_leg(device, with_cpu=not args.no_cpu_baseline)
-    cluster = None
+    cluster = corpus = None
     if world > 1 and not args.no_ahc:
         try:
             cluster = cluster_leg(device, rank, world)
         except Exception as e:
             cluster = {"error": f"{type(e).__name__}: {e}"[:300]}
+        try:
+            del audio, host_audio
+            torch.cuda.empty_cache()
+            corpus = corpus_leg(enc, device, rank, world)
+        except Exception as e:
+            corpus = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         if cluster is not None:
             line["cluster"] = cluster
+        if corpus is not None:
+            line["corpus_8h"] = corpus
         emit(line)
     if world > 1:
         dist.barrier()

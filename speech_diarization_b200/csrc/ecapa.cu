@@ -245,8 +245,10 @@ int setup_tdnn_gemm(GemmParams& P, const __half* A, long rows, int a_cols, int l
   P.num_kiters = ki;
   EpiParams& E = P.epi;
   E.flags = flags;
+#if SD_EXPERIMENTS
   if (const char* e = getenv("SD_ECAPA_APF")) P.a_prefetch = atoi(e) < 0 ? 0 : atoi(e) > 64 ? 64 : atoi(e);
   if (const char* e = getenv("SD_DEBUG_EPI")) E.flags |= (atoi(e) == 1 ? 64 : atoi(e) == 2 ? 128 : atoi(e) == 3 ? 256 : 0);
+#endif
   E.M_rows = (int)rows;
   E.N_cols = cout;
   E.Tp = pr.Tp;
@@ -472,7 +474,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
     pr.mfa.idesc = make_idesc_f16(256, 0, 256);
     for (int b = 0; b < 3; ++b) pr.tdnn1[b].idesc = pr.tdnn2[b].idesc = make_idesc_f16(256, 0, 256);
   }
-  if (p->use_chain) {   // device copy of the step table, only for the cooperative chain variant
+  if (SD_EXPERIMENTS && p->use_chain) {   // device copy of the step table, only for the cooperative chain variant
     std::vector<GemmParams> chain;
     for (int b = 0; b < 3; ++b) {
       chain.push_back(pr.tdnn1[b]);
@@ -553,10 +555,16 @@ int launch_res2net_fused(const Res2Params& Q, cudaStream_t st, bool use_pipe) {
   // 2: requested before the accumulator wait / one chunk ahead (0.163 ms); 3 (default): 2 + the frames beyond 127
   // computed transposed, their epilogue spread over all eight warps (0.148 ms); 1: 2 + direct row-per-lane stores of
   // y_i without the staging tile (measured SLOWER: 0.192 ms — the 16-byte pieces of 32 different lines per store)
+#if SD_EXPERIMENTS
   static const int mode = [] { const char* e = getenv("SD_R2_MODE"); return e ? atoi(e) : 3; }();
   void (*const kern)(const Res2Params) = mode == 0 ? res2net_fused_kernel<0> : mode == 2 ? res2net_fused_kernel<2> : mode == 3 ? res2net_fused_kernel<3> : res2net_fused_kernel<1>;
+  const auto all_modes = {res2net_fused_kernel<0>, res2net_fused_kernel<1>, res2net_fused_kernel<2>, res2net_fused_kernel<3>};
+#else
+  void (*const kern)(const Res2Params) = res2net_fused_kernel<3>;
+  const auto all_modes = {res2net_fused_kernel<3>};
+#endif
   if (attr_needed(attr_done)) {
-    for (auto k : {res2net_fused_kernel<0>, res2net_fused_kernel<1>, res2net_fused_kernel<2>, res2net_fused_kernel<3>})
+    for (auto k : all_modes)
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, R2_SMEM) != cudaSuccess ||
           cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
                                cudaSharedmemCarveoutMaxShared) != cudaSuccess)
@@ -672,7 +680,9 @@ int launch_res2net_fused(const Res2Params& Q, cudaStream_t st, bool use_pipe) {
 // the 256-wide TDNN GEMMs (block0, tdnn1/2, MFA): 2-CTA multicast variant unless disabled
 int launch_big(SdEcapaPlan* p, const GemmParams& P, cudaStream_t st) {
   if (p->use_2sm) return launch_gemm_2sm(P, st);
+#if SD_EXPERIMENTS
   if (p->use_mc) return launch_gemm_mc_t<EPI_TDNN, 256>(P, st);
+#endif
   return launch_gemm<EPI_TDNN>(P, st);
 }
 
@@ -707,11 +717,13 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st, bool skip_front = f
     if (skip_front && b == 0) {
       mark(p, st);
       mark(p, st);
+#if SD_EXPERIMENTS
     } else if (p->use_chain) {
       // tdnn1 -> 7 dependent Res2Net convs -> tdnn2 in ONE cooperative launch (grid barrier between steps)
       SD_TRY((launch_gemm_chain<EPI_TDNN, 256>(pr.chain_dev + 9 * b, 9, st)));
       mark(p, st);
       mark(p, st);
+#endif
     } else {
       SD_TRY(launch_big(p, pr.tdnn1[b], st));
       mark(p, st);
@@ -834,16 +846,16 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   for (int i = 0; i < n_tensors; ++i) sd.m[names[i]] = {tensors[i], numels[i]};
   SdEcapaPlan* p = new SdEcapaPlan;
   p->max_batch = max_batch;
-  if (const char* e = getenv("SD_ECAPA_CHAIN")) p->use_chain = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_CHAIN")) p->use_chain = SD_EXPERIMENTS && atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_GRAPH")) p->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_CONV3")) p->use_conv3 = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_R2FUSED")) p->use_r2fused = atoi(e) != 0;
   if (const char* e = getenv("SD_R2_PIPE")) p->use_r2pipe = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_COLSUM")) p->use_colsum = atoi(e) != 0;
-  if (const char* e = getenv("SD_ECAPA_TMAOUT")) p->use_tma_out = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_TMAOUT")) p->use_tma_out = SD_EXPERIMENTS && atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_KSPLIT")) p->ksplit = atoi(e) < 1 ? 1 : atoi(e) > KSPLIT_MAX ? KSPLIT_MAX : atoi(e);
   if (const char* e = getenv("SD_ECAPA_L2ORDER")) p->use_l2_order = atoi(e) != 0;
-  if (const char* e = getenv("SD_ECAPA_MC")) p->use_mc = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_MC")) p->use_mc = SD_EXPERIMENTS && atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_2SM")) p->use_2sm = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_PDL")) p->use_pdl = atoi(e) != 0;
   if (p->use_chain) p->use_mc = p->use_2sm = false;  // the cooperative chain uses the plain kernels

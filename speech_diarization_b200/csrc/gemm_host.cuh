@@ -134,6 +134,7 @@ inline int launch_gemm_t(const GemmParams& P, cudaStream_t stream) {
   return SD_OK;
 }
 
+#if SD_EXPERIMENTS
 // 2-CTA-cluster launch with the B tile multicast (gemm_tc_mc_kernel).  tmapB's box must hold n_tile / 2 rows.
 template <int EPI, int MAX_BN>
 inline int launch_gemm_mc_t(const GemmParams& P, cudaStream_t stream) {
@@ -168,6 +169,8 @@ inline int launch_gemm_mc_t(const GemmParams& P, cudaStream_t stream) {
   return SD_OK;
 }
 
+#endif  // SD_EXPERIMENTS
+
 // cta_group::2 launch (gemm_tc_2sm_kernel): EPI_TDNN, n_tile = 256, idesc with M = 256, tmapB box = 128 rows.
 inline int launch_gemm_2sm(const GemmParams& P, cudaStream_t stream) {
   using Cfg = Cfg2sm;
@@ -194,7 +197,7 @@ inline int launch_gemm_2sm(const GemmParams& P, cudaStream_t stream) {
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_flag() ? 2 : 1;
-  static const char* const trace_path = getenv("SD_GEMM_TRACE");   // read once: this runs per launch
+  static const char* const trace_path = SD_TRACE_ON ? getenv("SD_GEMM_TRACE") : nullptr;   // read once: this runs per launch
   if (const char* path = trace_path) {   // debug: clock stamps of CTA 0 for launches with num_kiters == SD_GEMM_TRACE_K
     static const char* const ks = getenv("SD_GEMM_TRACE_K");
     if (P.num_kiters == (ks ? atoi(ks) : 16)) {
@@ -245,6 +248,7 @@ inline int launch_gemm(const GemmParams& P, cudaStream_t stream) {
   }
 }
 
+#if SD_EXPERIMENTS
 // Cooperative launch of a chain of dependent GEMMs (gemm_chain_kernel); `dev_steps` is a device
 // array of num_steps GemmParams.  n_tile of every step must fit MAX_BN.
 template <int EPI, int MAX_BN>
@@ -262,6 +266,8 @@ inline int launch_gemm_chain(const GemmParams* dev_steps, int num_steps, cudaStr
   if (e != cudaSuccess) return fail(SD_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
   return SD_OK;
 }
+
+#endif  // SD_EXPERIMENTS
 
 inline void init_params(GemmParams& P) {
   std::memset(&P, 0, sizeof(P));

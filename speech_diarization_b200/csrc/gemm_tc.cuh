@@ -276,7 +276,9 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
     __syncwarp();
     tmem_ld32(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
     tmem_ld_wait();
+#if SD_EXPERIMENTS
     if (E.flags & 64) continue;  // TIMING PROBE ONLY (SD_DEBUG_EPI=1): skip the epilogue math and stores
+#endif
     const int col0 = n_blk * P.n_tile + c0;  // column within this layer's output
     float x[32];
     const float4* b4 = reinterpret_cast<const float4*>(sp + c0);
@@ -310,7 +312,9 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
       pk[q].z = pack_half2(x[8 * q + 4], x[8 * q + 5]);
       pk[q].w = pack_half2(x[8 * q + 6], x[8 * q + 7]);
     }
+#if SD_EXPERIMENTS
     if (E.flags & 128) continue;  // TIMING PROBE ONLY (SD_DEBUG_EPI=2): math but no stores
+#endif
     // -> staging (every row, valid or not: tdnn_writeout skips what must not be written)
     const int chunk = c0 >> 6;           // 64-column chunk of the tile
     const int p0 = (c0 >> 5 & 1) * 4;    // first 16-byte piece of this 32-column run inside the 128 B row
@@ -363,7 +367,9 @@ __device__ __forceinline__ void epilogue_tdnn(const GemmParams& P, int m_blk, in
 __device__ __forceinline__ void tdnn_writeout(const GemmParams& P, int m_blk, int n_blk,
                                               const uint8_t* stage_out, int et) {
   const EpiParams& E = P.epi;
+#if SD_EXPERIMENTS
   if (E.flags & (64 | 128 | 256)) return;  // TIMING/DEBUG PROBES (SD_DEBUG_EPI)
+#endif
   const int sub = et & 7;    // 16-byte piece of the 128-byte row chunk
   const int rsub = et >> 3;  // row within a 32-row pass
   const int nchunks = P.n_tile >> 6;
@@ -1117,6 +1123,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
   gemm_teardown(c);
 }
 
+#if SD_EXPERIMENTS
 // The same GEMM on 2-CTA clusters with the B tile multicast (launched with cluster dims {2,1,1}).
 template <int EPI, int MAX_BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -1128,6 +1135,8 @@ gemm_tc_mc_kernel(const __grid_constant__ GemmParams P) {
   gemm_run<EPI, MAX_BN, true>(P, c, ps);
   gemm_teardown<true>(c);
 }
+
+#endif  // SD_EXPERIMENTS
 
 // ------------------------------------------------------------------------------------------------
 // cta_group::2 variant for the 256-wide TDNN GEMMs (block0, tdnn1/2, MFA): two CTAs (a cluster) own a
@@ -1144,7 +1153,7 @@ struct Cfg2sm {
   static constexpr int B_BYTES = 128 * BK * 2;            // 16 KB: this CTA's half of the 256-row B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
 #ifndef SD_TRACE_ON
-#define SD_TRACE_ON 1   // clock-stamp trace of the cta_group::2 kernel compiled in (GemmParams::trace, null in production)
+#define SD_TRACE_ON SD_EXPERIMENTS   // clock-stamp trace of the cta_group::2 kernel (GemmParams::trace, tools/gemm_trace.py)
 #endif
 #ifndef SD_2SM_STAGES
 #define SD_2SM_STAGES 4
@@ -1212,7 +1221,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
       // ring holds 128 KB in flight per SM, which covers ~2000 cycles of load latency at one k-iteration per 512
       // cycles only just (SD_GEMM_TRACE: the MMA thread waits on full[] — 650 cycles per k-iteration); A streams from
       // HBM, so the ring is effectively deepened in L2, where it costs no shared memory.  (B, the weights, is L2-resident.)
-      const int pf = P.a_prefetch;
+      const int pf = SD_EXPERIMENTS ? P.a_prefetch : 0;
       int pf_tile = tile0, pf_k = 0;
       auto prefetch_next = [&]() {
         if (pf_tile >= num_tiles) return;
@@ -1278,7 +1287,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;
-    const bool tma_out = (P.epi.flags & EF_TMA_OUT) != 0;
+    const bool tma_out = SD_EXPERIMENTS && (P.epi.flags & EF_TMA_OUT) != 0;
     if (tma_out && et == 0) {
       tma_prefetch_desc(&P.tmapH);
       if (P.epi.out2 != nullptr) tma_prefetch_desc(&P.tmapO2);
@@ -1354,6 +1363,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
   }
 }
 
+#if SD_EXPERIMENTS
 // A CHAIN of dependent GEMMs in one cooperative launch: step s+1 reads what step s wrote
 // (Res2Net: y_i = TDNN_i(x_i + y_{i-1}); around it the block's two 1x1 TDNNs).  Between steps
 // the whole grid synchronises; the generic-proxy stores of the epilogues are made visible to
@@ -1379,5 +1389,7 @@ gemm_chain_kernel(const GemmParams* __restrict__ steps, int num_steps) {
   }
   gemm_teardown(c);
 }
+
+#endif  // SD_EXPERIMENTS
 
 }  // namespace sd

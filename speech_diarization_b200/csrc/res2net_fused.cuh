@@ -69,11 +69,11 @@ struct alignas(64) Res2Params {
 
 // finer stamps inside the chunks of epilogue warp 4 (quarter 0: two M-tile passes)
 __device__ __forceinline__ void r2_stamp2(const Res2Params& P, int n, int k, int s) {
-  if (P.trace != nullptr && blockIdx.x == 0 && n < 32 && (threadIdx.x >> 5) == 4 && (threadIdx.x & 31) == 0)
+  if (SD_EXPERIMENTS && P.trace != nullptr && blockIdx.x == 0 && n < 32 && (threadIdx.x >> 5) == 4 && (threadIdx.x & 31) == 0)
     P.trace[32 * 18 + (n * 4 + k) * 8 + s] = clock64();
 }
 __device__ __forceinline__ void r2_stamp(const Res2Params& P, int n, int slot) {
-  if (P.trace != nullptr && blockIdx.x == 0 && n < 32) P.trace[n * 18 + slot] = clock64();
+  if (SD_EXPERIMENTS && P.trace != nullptr && blockIdx.x == 0 && n < 32) P.trace[n * 18 + slot] = clock64();
 }
 
 // MODE 0: y_i goes through a per-warp staging tile and leaves as 64-byte row segments, 8 rows per store
@@ -172,10 +172,10 @@ res2net_fused_kernel(const __grid_constant__ Res2Params P) {
           r2_stamp(P, n, 0);
           for (int kc = 0; kc < 2; ++kc)
             for (int j = 0; j < 3; ++j) {
-              if (P.trace != nullptr && blockIdx.x == 0 && n < 32) P.trace[1600 + n * 12 + (kc * 3 + j) * 2] = clock64();
+              if (SD_EXPERIMENTS && P.trace != nullptr && blockIdx.x == 0 && n < 32) P.trace[1600 + n * 12 + (kc * 3 + j) * 2] = clock64();
               mbar_wait(&w_full[slot], ph);
               tc_fence_after();
-              if (P.trace != nullptr && blockIdx.x == 0 && n < 32) P.trace[1600 + n * 12 + (kc * 3 + j) * 2 + 1] = clock64();
+              if (SD_EXPERIMENTS && P.trace != nullptr && blockIdx.x == 0 && n < 32) P.trace[1600 + n * 12 + (kc * 3 + j) * 2 + 1] = clock64();
               const uint64_t db = make_smem_desc_sw128(smem_u32(wring + slot * R2_WBOX));
               if (MODE == 3 && n_mt > 1) {
                 // frames 128.. transposed: "A" = the weight box (128 output channels), "B" = 32 rows of the input

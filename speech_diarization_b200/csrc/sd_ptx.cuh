@@ -312,6 +312,12 @@ __device__ __forceinline__ __half half_sat(float a) {
   asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(a));
   return __ushort_as_half(r);
 }
+// SD_EXPERIMENTS=1 compiles the measured-and-rejected variants and the timing probes back in (cooperative chain
+// kernel, multicast GEMM, TMA-store write-out, L2 prefetch of A, SD_DEBUG_EPI, the older fused Res2Net modes, kernel
+// traces).  The default build carries only the code that runs.
+#ifndef SD_EXPERIMENTS
+#define SD_EXPERIMENTS 0
+#endif
 constexpr float kHalfMax = 65504.f;
 #ifndef SD_NO_OFLOW
 #define SD_NO_OFLOW 0     // 1: A/B build without the overflow tracking (timing only)

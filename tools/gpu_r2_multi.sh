@@ -13,3 +13,8 @@ d = json.load(open("gpurun_out/bench_${N}gpu.json"))
 print({k: d[k] for k in ("value", "ms_per_step", "n_gpus")}, "e2e", d["e2e"]["value"])
 print("cluster", json.dumps(d.get("cluster")))
 PY
+python - <<PY
+import json
+d = json.load(open("gpurun_out/bench_${N}gpu.json"))
+print("corpus", json.dumps(d.get("corpus_8h")))
+PY
