@@ -38,7 +38,7 @@ namespace {
 constexpr int AHC_THREADS = 256;
 
 struct AhcState {
-  double* D;        // [N, N]
+  void* D;          // [N, N] working matrix, f64 or f32 (ahc_rounds_kernel<U, MT>)
   double* nn_dist;  // [N]
   int* nn_idx;      // [N]
   int* size;        // [N]
@@ -62,9 +62,10 @@ __device__ __forceinline__ long long ahc_now() {
   return t;
 }
 
-// f32 [N,N] -> f64 [N,N], symmetrised from the upper triangle (sklearn reads D[i,j], i<j).
+// f32 [N,N] -> working matrix [N,N] (f64 or f32), symmetrised from the upper triangle (sklearn reads D[i,j], i<j).
+template <typename MT>
 __global__ void __launch_bounds__(256)
-ahc_init_matrix_kernel(const float* __restrict__ dist, int N, double* __restrict__ D) {
+ahc_init_matrix_kernel(const float* __restrict__ dist, int N, MT* __restrict__ D) {
   __shared__ float tile[32][33];
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bi > bj) return;
@@ -113,10 +114,14 @@ __device__ __forceinline__ void argmin_combine(double& d, int& i, double od, int
   if (od < d || (od == d && oi < i)) { d = od; i = oi; }
 }
 
-// AHC_U = independent row entries in flight per thread (phases A, C1, C3)
-template <int AHC_U>
+// AHC_U = independent row entries in flight per thread (phases A, C1, C3).  MT = storage type of the working matrix:
+// double (default: scipy's arithmetic exactly) or float (SD_AHC_F32=1: every Lance-Williams update is still computed in
+// f64 but STORED rounded to f32 — half the bytes per round; merge heights then differ from scipy's by ~1e-7 relative,
+// which can only matter for ties closer than that)
+template <int AHC_U, typename MT>
 __global__ void __launch_bounds__(AHC_THREADS)
 ahc_rounds_kernel(AhcState S) {
+  MT* const DM = static_cast<MT*>(S.D);
   cg::grid_group grid = cg::this_grid();
   __shared__ double red_d[AHC_THREADS / 32];
   __shared__ int red_i[AHC_THREADS / 32];
@@ -153,7 +158,7 @@ ahc_rounds_kernel(AhcState S) {
     }
     for (int q = blockIdx.x; q < n_dirty; q += gridDim.x) {
       const int r = S.dirty_list[q];
-      const double* row = S.D + static_cast<size_t>(r) * N;
+      const MT* row = DM + static_cast<size_t>(r) * N;
       double bd = 1e300;
       int bi = 0x7fffffff;
       // AHC_U independent list -> (distance, liveness) chains in flight per thread: one entry at a time is a chain
@@ -216,8 +221,8 @@ ahc_rounds_kernel(AhcState S) {
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const int i = S.pair_i[p], j = S.pair_j[p];
       const double ni = S.size[i], nj = S.size[j], inv = ni + nj;
-      double* ri = S.D + static_cast<size_t>(i) * N;
-      const double* rj = S.D + static_cast<size_t>(j) * N;
+      MT* ri = DM + static_cast<size_t>(i) * N;
+      const MT* rj = DM + static_cast<size_t>(j) * N;
       for (int q0 = tid; q0 < n_list; q0 += AHC_THREADS * AHC_U) {
         int k[AHC_U];
         double a[AHC_U], b[AHC_U];
@@ -231,7 +236,7 @@ ahc_rounds_kernel(AhcState S) {
           if (k[u] >= 0) { a[u] = ri[k[u]]; b[u] = rj[k[u]]; }
 #pragma unroll
         for (int u = 0; u < AHC_U; ++u)
-          if (k[u] >= 0) ri[k[u]] = (ni * a[u] + nj * b[u]) / inv;
+          if (k[u] >= 0) ri[k[u]] = static_cast<MT>((ni * a[u] + nj * b[u]) / inv);
       }
       // ---- C2: corners between two merged clusters (upper triangle only, i_p < i_q).  They combine two entries of
       // THIS row, both just written by this CTA, so a CTA barrier is enough (this used to be a phase of its own)
@@ -240,7 +245,7 @@ ahc_rounds_kernel(AhcState S) {
         const int iq = S.pair_i[q], jq = S.pair_j[q];
         if (i < iq) {
           const double nq = S.size[iq], mq = S.size[jq];
-          ri[iq] = (nq * ri[iq] + mq * ri[jq]) / (nq + mq);
+          ri[iq] = static_cast<MT>((nq * static_cast<double>(ri[iq]) + mq * static_cast<double>(ri[jq])) / (nq + mq));
         }
       }
     }
@@ -249,10 +254,10 @@ ahc_rounds_kernel(AhcState S) {
     // ---- C3: mirror row i_p into column i_p (and the lower corners from the upper ones)
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const int i = S.pair_i[p];
-      double* ri = S.D + static_cast<size_t>(i) * N;
+      MT* ri = DM + static_cast<size_t>(i) * N;
       for (int q0 = tid; q0 < n_list; q0 += AHC_THREADS * AHC_U) {
         int k[AHC_U], rk[AHC_U], act[AHC_U];
-        double v[AHC_U];
+        MT v[AHC_U];
 #pragma unroll
         for (int u = 0; u < AHC_U; ++u) {
           const int q = q0 + u * AHC_THREADS;
@@ -267,8 +272,8 @@ ahc_rounds_kernel(AhcState S) {
         for (int u = 0; u < AHC_U; ++u) {
           if (!act[u]) continue;
           if (rk[u] >= 0 && (rk[u] & 1)) continue;  // absorbed this round
-          if (rk[u] >= 0 && k[u] < i) ri[k[u]] = S.D[static_cast<size_t>(k[u]) * N + i];
-          else S.D[static_cast<size_t>(k[u]) * N + i] = v[u];
+          if (rk[u] >= 0 && k[u] < i) ri[k[u]] = DM[static_cast<size_t>(k[u]) * N + i];
+          else DM[static_cast<size_t>(k[u]) * N + i] = v[u];
         }
       }
     }
@@ -411,7 +416,7 @@ extern "C" int sd_ahc_average_f32(const float* dist_dev, int N, double threshold
   AhcState S;
   S.N = N;
   S.thr = threshold;  // f64, as sklearn compares the f64 linkage distances with a Python float
-  S.D = reinterpret_cast<double*>(base + L.off_D);
+  S.D = base + L.off_D;
   S.nn_dist = reinterpret_cast<double*>(base + L.off_nn_dist);
   int* ip = reinterpret_cast<int*>(base + L.off_ints);
   S.nn_idx = ip;
@@ -427,8 +432,11 @@ extern "C" int sd_ahc_average_f32(const float* dist_dev, int N, double threshold
   S.act_list = ip + 8 * static_cast<size_t>(N) + 64;
   S.prof = getenv("SD_AHC_PROF") ? reinterpret_cast<long long*>(S.counters + 16) : nullptr;
 
+  // SD_AHC_F32=1: f32 working matrix (see ahc_rounds_kernel)
+  static const bool f32_store = [] { const char* e = getenv("SD_AHC_F32"); return e && atoi(e) != 0; }();
   const int nb = (N + 31) / 32;
-  ahc_init_matrix_kernel<<<dim3(nb, nb), 256, 0, st>>>(dist_dev, N, S.D);
+  if (f32_store) ahc_init_matrix_kernel<float><<<dim3(nb, nb), 256, 0, st>>>(dist_dev, N, static_cast<float*>(S.D));
+  else ahc_init_matrix_kernel<double><<<dim3(nb, nb), 256, 0, st>>>(dist_dev, N, static_cast<double*>(S.D));
   ahc_init_state_kernel<<<(N + 255) / 256, 256, 0, st>>>(S);
   SD_CUDA_OK(cudaGetLastError());
 
@@ -439,7 +447,8 @@ extern "C" int sd_ahc_average_f32(const float* dist_dev, int N, double threshold
   // (64 / 80 / 128 registers -> 4 / 3 / 2 CTAs per SM).  Measured at N = 5k / 20k / 50k: U = 1 4.06 / 33.6 / 206 ms,
   // U = 4 3.37 / 25.5 / 149 ms, U = 8 3.48 / 27.3 / 160 ms.
   static const int unroll = [] { const char* e = getenv("SD_AHC_U"); return e ? atoi(e) : 4; }();
-  void (*kern)(AhcState) = unroll <= 1 ? ahc_rounds_kernel<1> : unroll <= 4 ? ahc_rounds_kernel<4> : ahc_rounds_kernel<8>;
+  void (*kern)(AhcState) = f32_store ? (unroll <= 1 ? ahc_rounds_kernel<1, float> : unroll <= 4 ? ahc_rounds_kernel<4, float> : ahc_rounds_kernel<8, float>)
+                                     : (unroll <= 1 ? ahc_rounds_kernel<1, double> : unroll <= 4 ? ahc_rounds_kernel<4, double> : ahc_rounds_kernel<8, double>);
   SD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, AHC_THREADS, 0));
   if (occ < 1) return fail(SD_ERR_CUDA, "ahc_rounds_kernel cannot be made resident");
   if (occ > 4) occ = 4;

@@ -1152,8 +1152,13 @@ struct Cfg2sm {
   static constexpr int A_BYTES = BM * BK * 2;             // 16 KB: this CTA's 128 rows of A
   static constexpr int B_BYTES = 128 * BK * 2;            // 16 KB: this CTA's half of the 256-row B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
+// Clock-stamp trace of the cta_group::2 kernel (GemmParams::trace, null in production; tools/gemm_trace.py).  It stays
+// compiled in although SD_EXPERIMENTS is off: the build WITH the (predicated-off) stamps is the faster one — re-measured
+// this round, three alternating runs each on one box: MFA 1.060-1.086 ms with, 1.112-1.132 ms without; tdnn1 + tdnn2
+// 0.97-0.99 vs 1.01-1.03 ms; block0 0.132-0.138 vs 0.124-0.126 ms (ptxas allocates 165 vs 163 registers and schedules
+// the epilogue differently).  Net 0.07 ms per step in favour of keeping them.
 #ifndef SD_TRACE_ON
-#define SD_TRACE_ON SD_EXPERIMENTS   // clock-stamp trace of the cta_group::2 kernel (GemmParams::trace, tools/gemm_trace.py)
+#define SD_TRACE_ON 1
 #endif
 #ifndef SD_2SM_STAGES
 #define SD_2SM_STAGES 4
