@@ -759,7 +759,7 @@ int trunk_body(SdEcapaPlan* p, Program& pr, cudaStream_t st, bool skip_front = f
   SD_TRY(launch_big(p, pr.mfa, st));
   mark(p, st);
   if (pr.colsum_ok)
-    SD_CUDA_OK(launch_pdl(colstats_finish_kernel, dim3(C3 / 256, B), dim3(256), 0, st, p->cs_mfa, p->cq_mfa, p->wmfa.shift,
+    SD_CUDA_OK(launch_pdl(colstats_finish_kernel, dim3(B), dim3(256), 0, st, p->cs_mfa, p->cq_mfa, p->wmfa.shift,
                           C3, Tp, T, pr.cs_group, p->stats, 2 * C3, p->stats + C3, p->stats_h));
   else
     SD_CUDA_OK(launch_pdl(time_mean_std_kernel, dim3(C3 / 256, B), dim3(128), 0, st, p->h, C3, Tp, T, HALO, C3, p->stats,

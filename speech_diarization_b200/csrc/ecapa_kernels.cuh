@@ -111,7 +111,7 @@ time_mean_std_kernel(const __half* __restrict__ x, int ld, int Tp, int T, int H,
 // at index (r / 128) * (128 / G) + (r % 128) / G.  The groups are added in ascending j, so the result does not
 // depend on which batch slot the window occupies.  mean = k + S/T, var = (Q - S^2/T)/T (shift-invariant),
 // std = sqrt(max(var, 1e-12)).
-// grid (C/256, B), block 256.  std_out / out_h may be null; out_h gets [mean | std] as f16 when std is wanted.
+// grid B, block 256.  std_out / out_h may be null; out_h gets [mean | std] as f16 when std is wanted.
 __device__ __forceinline__ size_t cs_group_index(int b, int j, int Tp, int G) {
   const int r = b * Tp + j * G;
   return static_cast<size_t>(r >> 7) * (128 / G) + (r & 127) / G;
@@ -124,33 +124,47 @@ colstats_finish_kernel(const float* __restrict__ colsum, const float* __restrict
                        __half* __restrict__ out_h) {
   pdl_trigger();
   pdl_wait();
-  const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= C) return;
-  float S = 0.f, Q = 0.f;
+  // grid = B (one CTA per window), four channels per thread and pass: every group's 16-byte loads of both
+  // statistics are in flight together (the first version — one channel per thread, one load at a time — spent 31 us
+  // on 63 MB)
+  const int b = blockIdx.x;
   const int ng = Tp / G;
-  for (int j0 = 0; j0 < ng; j0 += 8) {     // eight groups' loads in flight, added in ascending order
-    float vs[8], vq[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const bool ok = j0 + e < ng;
-      const size_t o = ok ? cs_group_index(b, j0 + e, Tp, G) * C + c : 0;
-      vs[e] = ok ? colsum[o] : 0.f;
-      vq[e] = ok && colsq != nullptr ? colsq[o] : 0.f;
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (j0 + e < ng) { S += vs[e]; Q += vq[e]; }
-  }
-  const float k = shift != nullptr ? __half2float(__float2half_rn(shift[c])) : 0.f;
   const float inv = 1.0f / static_cast<float>(T);
-  const float mean = k + S * inv;
-  mean_out[static_cast<size_t>(b) * ld_out + c] = mean;
-  if (std_out != nullptr) {
-    const float sd = sqrtf(fmaxf((Q - S * S * inv) * inv, 1e-12f));
-    std_out[static_cast<size_t>(b) * ld_out + c] = sd;
-    if (out_h != nullptr) {
-      out_h[static_cast<size_t>(b) * ld_out + c] = half_sat(mean);
-      out_h[static_cast<size_t>(b) * ld_out + C + c] = half_sat(sd);
+  for (int c = threadIdx.x * 4; c < C; c += 1024) {
+    float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < ng; j0 += 8) {     // eight groups at a time, added in ascending order (slot-invariant)
+      float4 vs[8], vq[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool ok = j0 + e < ng;
+        const size_t o = ok ? cs_group_index(b, j0 + e, Tp, G) * C + c : 0;
+        vs[e] = ok ? *reinterpret_cast<const float4*>(colsum + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vq[e] = ok && colsq != nullptr ? *reinterpret_cast<const float4*>(colsq + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (j0 + e < ng) {
+          S.x += vs[e].x; S.y += vs[e].y; S.z += vs[e].z; S.w += vs[e].w;
+          Q.x += vq[e].x; Q.y += vq[e].y; Q.z += vq[e].z; Q.w += vq[e].w;
+        }
+    }
+    float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (shift != nullptr) {
+      const float4 sh = *reinterpret_cast<const float4*>(shift + c);
+      k = make_float4(__half2float(__float2half_rn(sh.x)), __half2float(__float2half_rn(sh.y)),
+                      __half2float(__float2half_rn(sh.z)), __half2float(__float2half_rn(sh.w)));
+    }
+    const float4 mean = make_float4(k.x + S.x * inv, k.y + S.y * inv, k.z + S.z * inv, k.w + S.w * inv);
+    *reinterpret_cast<float4*>(mean_out + static_cast<size_t>(b) * ld_out + c) = mean;
+    if (std_out != nullptr) {
+      const float4 sd = make_float4(sqrtf(fmaxf((Q.x - S.x * S.x * inv) * inv, 1e-12f)), sqrtf(fmaxf((Q.y - S.y * S.y * inv) * inv, 1e-12f)),
+                                    sqrtf(fmaxf((Q.z - S.z * S.z * inv) * inv, 1e-12f)), sqrtf(fmaxf((Q.w - S.w * S.w * inv) * inv, 1e-12f)));
+      *reinterpret_cast<float4*>(std_out + static_cast<size_t>(b) * ld_out + c) = sd;
+      if (out_h != nullptr) {
+        __half* oh = out_h + static_cast<size_t>(b) * ld_out;
+        *reinterpret_cast<uint2*>(oh + c) = make_uint2(pack_half2(mean.x, mean.y), pack_half2(mean.z, mean.w));
+        *reinterpret_cast<uint2*>(oh + C + c) = make_uint2(pack_half2(sd.x, sd.y), pack_half2(sd.z, sd.w));
+      }
     }
   }
 }
@@ -181,16 +195,6 @@ se_gate_kernel(const float* __restrict__ colsum, const float* __restrict__ shift
   const int nb = min(SEG, B - b0);
   // The kernel is a chain of L2 round trips (partial sums -> W1 -> W2), so every stage requests the next stage's
   // first operands before it starts its own arithmetic.
-  // layer 1: warp w owns hidden units 8w .. 8w+7, two at a time; a lane covers the channel octets lane + 32 st
-  uint4 wv[2][4];
-  auto load_w1 = [&](int j0) {
-#pragma unroll
-    for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-      for (int st = 0; st < 4; ++st)
-        wv[jj][st] = __ldg(reinterpret_cast<const uint4*>(W1h + static_cast<size_t>(j0 + jj) * SE_C) + lane + 32 * st);
-  };
-  load_w1(warp * 8);
   // ---- squeeze: thread -> (window u = tid / 128 .. , 4 channels); all of a window's groups requested together
   {
     const int c = (tid & 255) * 4;
@@ -227,43 +231,52 @@ se_gate_kernel(const float* __restrict__ colsum, const float* __restrict__ shift
     }
   }
   __syncthreads();
-  // ---- excitation layer 1
+  // ---- excitation layer 1: warp w owns hidden units 8w .. 8w+7; a lane covers the channel octets lane + 32 st.
+  // Per st the four windows' means of the octet sit in registers (8 LDS.128) and are used for all eight units
+  // (256 FMA): the first version read them from shared memory per unit pair and was bound by the LDS pipe
+  // (stall_short_sb + stall_mio = 43 % of the samples).
   const int c2 = (tid & 255) * 4;
   const int jhalf = (tid >> 8) * (SE_S / 2);          // threads 0-255 take hidden units 0-63, 256-511 take 64-127
-  for (int jq = 0; jq < 4; ++jq) {
-    const int j0 = warp * 8 + jq * 2;
-    float acc[2][SEG];
+  {
+    float acc[8][SEG];
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj)
+    for (int jj = 0; jj < 8; ++jj)
 #pragma unroll
       for (int u = 0; u < SEG; ++u) acc[jj][u] = 0.f;
+    const uint4* const wrow = reinterpret_cast<const uint4*>(W1h + static_cast<size_t>(warp * 8) * SE_C) + lane;
 #pragma unroll
     for (int st = 0; st < 4; ++st) {
+      uint4 wv[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) wv[jj] = __ldg(wrow + jj * (SE_C / 8) + 32 * st);
+      float4 m0[SEG], m1[SEG];
       const int c8 = (lane + 32 * st) * 8;
 #pragma unroll
       for (int u = 0; u < SEG; ++u) {
-        const float4 m0 = *reinterpret_cast<const float4*>(sm_mean + u * SE_C + c8);
-        const float4 m1 = *reinterpret_cast<const float4*>(sm_mean + u * SE_C + c8 + 4);
+        m0[u] = *reinterpret_cast<const float4*>(sm_mean + u * SE_C + c8);
+        m1[u] = *reinterpret_cast<const float4*>(sm_mean + u * SE_C + c8 + 4);
+      }
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          const __half2* wh = reinterpret_cast<const __half2*>(&wv[jj][st]);
-          const float2 w0 = __half22float2(wh[0]), w1 = __half22float2(wh[1]);
-          const float2 w2f = __half22float2(wh[2]), w3 = __half22float2(wh[3]);
+      for (int jj = 0; jj < 8; ++jj) {
+        const __half2* wh = reinterpret_cast<const __half2*>(&wv[jj]);
+        const float2 w0 = __half22float2(wh[0]), w1 = __half22float2(wh[1]);
+        const float2 w2f = __half22float2(wh[2]), w3 = __half22float2(wh[3]);
+#pragma unroll
+        for (int u = 0; u < SEG; ++u) {
           float a = acc[jj][u];
-          a = fmaf(w0.x, m0.x, a); a = fmaf(w0.y, m0.y, a); a = fmaf(w1.x, m0.z, a); a = fmaf(w1.y, m0.w, a);
-          a = fmaf(w2f.x, m1.x, a); a = fmaf(w2f.y, m1.y, a); a = fmaf(w3.x, m1.z, a); a = fmaf(w3.y, m1.w, a);
+          a = fmaf(w0.x, m0[u].x, a); a = fmaf(w0.y, m0[u].y, a); a = fmaf(w1.x, m0[u].z, a); a = fmaf(w1.y, m0[u].w, a);
+          a = fmaf(w2f.x, m1[u].x, a); a = fmaf(w2f.y, m1[u].y, a); a = fmaf(w3.x, m1[u].z, a); a = fmaf(w3.y, m1[u].w, a);
           acc[jj][u] = a;
         }
       }
     }
-    if (jq < 3) load_w1(j0 + 2);           // wv is free again: the next two units, under the reductions below
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      const float bj = __ldg(b1 + j0 + jj);
+    for (int jj = 0; jj < 8; ++jj) {
+      const float bj = __ldg(b1 + warp * 8 + jj);
 #pragma unroll
       for (int u = 0; u < SEG; ++u) {
         const float a = warp_sum(acc[jj][u]);
-        if (lane == 0) sm_hid[u * SE_S + j0 + jj] = fmaxf(a + bj, 0.f);
+        if (lane == 0) sm_hid[u * SE_S + warp * 8 + jj] = fmaxf(a + bj, 0.f);
       }
     }
   }
@@ -286,16 +299,22 @@ se_gate_kernel(const float* __restrict__ colsum, const float* __restrict__ shift
           wn[q] = __ldg(reinterpret_cast<const uint2*>(W2th + static_cast<size_t>(jhalf + j + 16 + q) * SE_C + c2));
       }
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const float2 wa = __half22float2(*reinterpret_cast<const __half2*>(&w2[q].x));
-        const float2 wb = __half22float2(*reinterpret_cast<const __half2*>(&w2[q].y));
+      for (int q4 = 0; q4 < 16; q4 += 4) {
+        float4 hv[SEG];       // four hidden units of every window per (broadcast) 16-byte read
 #pragma unroll
-        for (int u = 0; u < SEG; ++u) {
-          const float h = sm_hid[u * SE_S + jhalf + j + q];
-          acc[u][0] = fmaf(h, wa.x, acc[u][0]);
-          acc[u][1] = fmaf(h, wa.y, acc[u][1]);
-          acc[u][2] = fmaf(h, wb.x, acc[u][2]);
-          acc[u][3] = fmaf(h, wb.y, acc[u][3]);
+        for (int u = 0; u < SEG; ++u) hv[u] = *reinterpret_cast<const float4*>(sm_hid + u * SE_S + jhalf + j + q4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 wa = __half22float2(*reinterpret_cast<const __half2*>(&w2[q4 + e].x));
+          const float2 wb = __half22float2(*reinterpret_cast<const __half2*>(&w2[q4 + e].y));
+#pragma unroll
+          for (int u = 0; u < SEG; ++u) {
+            const float h = e == 0 ? hv[u].x : e == 1 ? hv[u].y : e == 2 ? hv[u].z : hv[u].w;
+            acc[u][0] = fmaf(h, wa.x, acc[u][0]);
+            acc[u][1] = fmaf(h, wa.y, acc[u][1]);
+            acc[u][2] = fmaf(h, wb.x, acc[u][2]);
+            acc[u][3] = fmaf(h, wb.y, acc[u][3]);
+          }
         }
       }
       if (j + 16 < SE_S / 2) {
