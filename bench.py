@@ -608,18 +608,25 @@ def dense_pass_leg(enc, audio, device) -> dict:
 
 
 PEAK_HBM = 6450.9
-PEAK_TF = 1430.4
+PEAK_TF = 1670.0
+
+
+PEAK_TF_SUSTAINED = 1430.4
 
 
 def load_peaks():
-    global PEAK_HBM, PEAK_TF
+    """Roofline denominators.  The timed region is 20-40 steps of 3.5 ms at full clocks (1965 MHz, no power cap in the
+    NVML samples), so the dense-bf16 peak a launch is held against is the BURST figure of MEASURED_PEAKS.json
+    (cuBLAS best-of-10), not the figure sustained over seconds at ~1.38 GHz; the latter is reported beside it."""
+    global PEAK_HBM, PEAK_TF, PEAK_TF_SUSTAINED
     src = "fallback 6650 GB/s, 1590 TFLOP/s (B200_PROFILING.md)"
     try:
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        PEAK_HBM = float(pk["hbm_gbs"]); PEAK_TF = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
-        src = "MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained)"
+        PEAK_HBM = float(pk["hbm_gbs"]); PEAK_TF = float(pk["bf16_tflops"])
+        PEAK_TF_SUSTAINED = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
+        src = "MEASURED_PEAKS.json (hbm_gbs; bf16_tflops = burst, the launch is timed inside a ~0.1 s region at full clocks)"
     except Exception:
-        PEAK_HBM, PEAK_TF = 6650.0, 1590.0
+        PEAK_HBM, PEAK_TF, PEAK_TF_SUSTAINED = 6650.0, 1590.0, 1590.0
     return src
 
 
@@ -814,6 +821,7 @@ def main() -> None:
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_2sm_kernel<EPI_TDNN> (tcgen05 cta_group::2, 256x256 tile per CTA pair) — "
                                                       "MFA 1x1 conv 3072->3072, 50% of the trunk's FLOPs",
                          "achieved": achieved, "peak": PEAK_TF, "unit": "TFLOP/s", "frac": achieved / PEAK_TF,
+                         "peak_sustained": PEAK_TF_SUSTAINED, "frac_of_sustained": achieved / PEAK_TF_SUSTAINED,
                          "traffic": traffic, "algorithmic_flops_per_launch": mfa_flops, "launch_ms": mfa_ms,
                          "whole_step": {"tflops": step_flops / (ms_total / args.steps * 1e-3) / 1e12,
                                         "frac": step_flops / (ms_total / args.steps * 1e-3) / 1e12 / PEAK_TF,

@@ -46,9 +46,6 @@
 #ifndef SD_R2P_DBG
 #define SD_R2P_DBG 0     // timing probes (wrong results): 1 no global stores of y, 2 no loads of x_{i+1}, 4 no input-buffer stores
 #endif
-#ifndef SD_R2P_L2PF
-#define SD_R2P_L2PF 1    // L2 prefetch of the next convolution's x sub-band at the end of every epilogue
-#endif
 #ifndef SD_R2P_TRACE
 #define SD_R2P_TRACE 0   // 1: compile the clock-stamp trace in (Res2Params::trace, tools/r2p_trace.py); costs registers
 #endif
@@ -83,9 +80,9 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
   uint64_t* const bars = reinterpret_cast<uint64_t*>(wring + R2P_WSLOTS * R2_WBOX);
   uint64_t* const w_full = bars;            // [4] weight box landed
   uint64_t* const w_empty = bars + 4;       // [4] its MMAs retired
-  uint64_t* const a_full = bars + 8;        // [4] a window's first input landed (TMA)
-  uint64_t* const a_ready = bars + 12;      // [4] the epilogue wrote the next convolution's input (8 arrivals)
-  uint64_t* const a_free = bars + 16;       // [4] the window's last convolution has read its input
+  uint64_t* const x_full = bars + 8;        // [4] a slot's x tile landed (TMA): x_1 of a new window, or x_{i+2} after conv i
+  uint64_t* const a_ready = bars + 12;      // [4] the epilogue added y_i onto it: the next convolution's input is complete (8 arrivals)
+  uint64_t* const b_done = bars + 16;       // [4] a convolution's MMAs have finished reading the slot's buffer
   uint64_t* const t_full = bars + 20;       // [3] accumulator complete
   uint64_t* const t_empty = bars + 23;      // [3] accumulator drained (8 arrivals)
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
@@ -108,9 +105,9 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
         mbar_init(&w_empty[s], MC ? 2 : 1);     // MC: both CTAs of the pair must release a slot
       }
       for (int s = 0; s < R2P_SLOTS; ++s) {
-        mbar_init(&a_full[s], 1);
+        mbar_init(&x_full[s], 1);
         mbar_init(&a_ready[s], 8);
-        mbar_init(&a_free[s], 1);
+        mbar_init(&b_done[s], 1);
       }
       for (int a = 0; a < R2P_ACCS; ++a) {
         mbar_init(&t_full[a], 1);
@@ -133,22 +130,17 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
   auto window_of = [&](int r, int s) { return P.B - 1 - (static_cast<int>(blockIdx.x) + (r * R2P_SLOTS + s) * G); };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producers
+    // lane 0: the weight ring.  lane 1: the x tiles — x_1 of a window when its slot is taken over, and x_{i+2} into the
+    // slot's buffer as soon as convolution i's MMAs have finished reading it; the epilogue then only ADDS y_{i+1} onto
+    // it in shared memory.  (The first versions loaded x into registers in the epilogue: with one 16-frame block of
+    // look-ahead that was an exposed L2 / HBM round trip per block, 8.5 k of the epilogue's 17.5 k cycles.)
     if (lane == 0) {
-      tma_prefetch_desc(&P.tmapU);
       for (int i = 0; i < R2_CONVS; ++i) tma_prefetch_desc(MC ? &P.tmapWh[i] : &P.tmapW[i]);
       int slot = 0;
       uint32_t ph = 0;
       for (int r = 0; r < rounds_w; ++r) {
-        const int nact = max(0, min(R2P_SLOTS, n_mine - r * R2P_SLOTS));
         const int nact_w = min(R2P_SLOTS, n_pair - r * R2P_SLOTS);
-        for (int s = 0; s < nact; ++s) {
-          if (r > 0) mbar_wait(&a_free[s], (r - 1) & 1);   // the previous window's last convolution is done reading
-          mbar_arrive_expect_tx(&a_full[s], static_cast<uint32_t>(2 * RA * 128));
-          const int row0 = window_of(r, s) * Tp + H - d;
-          tma_load_2d(abuf + s * R2P_A_BYTES, &P.tmapU, &a_full[s], R2_SUB, row0);
-          tma_load_2d(abuf + s * R2P_A_BYTES + R2P_A_CHUNK, &P.tmapU, &a_full[s], R2_SUB + 64, row0);
-        }
         for (int i = 0; i < R2_CONVS; ++i)
           for (int s = 0; s < nact_w; ++s)
             for (int kc = 0; kc < 2; ++kc)
@@ -162,6 +154,20 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
                   tma_load_2d(wring + slot * R2_WBOX, &P.tmapW[i], &w_full[slot], j * R2_SUB + kc * 64, 0);
                 if (++slot == R2P_WSLOTS) { slot = 0; ph ^= 1; }
               }
+      }
+    } else if (lane == 1) {
+      tma_prefetch_desc(&P.tmapU);
+      for (int r = 0; r < rounds; ++r) {
+        const int nact = min(R2P_SLOTS, n_mine - r * R2P_SLOTS);
+        for (int i = 0; i < R2_CONVS; ++i)
+          for (int s = 0; s < nact; ++s) {
+            const int n = r * R2_CONVS + i;            // the slot's n-th tile: input base of its n-th convolution
+            if (n > 0) mbar_wait(&b_done[s], (n - 1) & 1);   // the slot's previous convolution is done reading
+            mbar_arrive_expect_tx(&x_full[s], static_cast<uint32_t>(2 * RA * 128));
+            const int row0 = window_of(r, s) * Tp + H - d;
+            tma_load_2d(abuf + s * R2P_A_BYTES, &P.tmapU, &x_full[s], (i + 1) * R2_SUB, row0);
+            tma_load_2d(abuf + s * R2P_A_BYTES + R2P_A_CHUNK, &P.tmapU, &x_full[s], (i + 1) * R2_SUB + 64, row0);
+          }
       }
     }
   } else if (warp == 1) {
@@ -187,7 +193,7 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
               }
               continue;
             }
-            if (i == 0) mbar_wait(&a_full[s], r & 1);
+            if (i == 0) mbar_wait(&x_full[s], (r * R2_CONVS) & 1);   // x_1 of a new window is the whole input
             else { mbar_wait(&a_ready[s], (ready_ph >> s) & 1u); ready_ph ^= 1u << s; }
             if (job >= R2P_ACCS) { mbar_wait(&t_empty[acc], (empty_ph >> acc) & 1u); empty_ph ^= 1u << acc; }
             tc_fence_after();
@@ -209,7 +215,7 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
                 if (++slot == R2P_WSLOTS) { slot = 0; ph ^= 1; }
               }
             umma_commit(&t_full[acc]);
-            if (i == R2_CONVS - 1) umma_commit(&a_free[s]);
+            umma_commit(&b_done[s]);
             if (SD_R2P_TRACE && P.trace != nullptr && blockIdx.x == 0 && job < 32) P.trace[job * 18 + 1] = clock64();
             if (++acc == R2P_ACCS) acc = 0;
             ++job;
@@ -245,23 +251,11 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
           uint8_t* const acol = abuf + s * R2P_A_BYTES + (quarter >> 1) * R2P_A_CHUNK;
           const bool has_next = i + 1 < R2_CONVS;
           const float cb = __ldg(P.bias[i] + ch), csc = __ldg(P.scale[i] + ch), csh = __ldg(P.shift[i] + ch);
-          const __half* const xs = P.u + (i + 2) * R2_SUB + tcol + (wrow + H) * ld;    // x_{i+1}, this lane's octet
           __half* const vrow = P.v + (i + 1) * R2_SUB + tcol + (wrow + H) * ld;        // y_i, this lane's octet
-          // x_{i+1} for this lane's octet, requested one 16-frame block ahead (block 0 before the accumulator wait).
-          // Three blocks ahead was measured and rejected: the 24 extra registers spill (96-register cap) and the
-          // epilogue got slower, 0.165 -> 0.206 ms per block.
-          uint4 xa[2];
-          auto load_x = [&](uint4 (&x2)[2], int fb) {
-#pragma unroll
-            for (int z = 0; z < 2; ++z) {
-              const int f = fb + tr + 8 * z;
-              if (f < T && !(SD_R2P_DBG & 2)) x2[z] = __ldg(reinterpret_cast<const uint4*>(xs + static_cast<size_t>(f) * ld));
-            }
-          };
-          if (has_next && n_blk > 0) load_x(xa, f_lo);       // requested before the accumulator wait
           const bool trc = SD_R2P_TRACE && P.trace != nullptr && blockIdx.x == 0 && job < 32 && lane == 0 && (gw == 0 || gw == 7);
           long long* const tp = P.trace + job * 18 + (gw == 0 ? 2 : 9);
           if (trc) tp[0] = clock64();
+          bool x_seen = false;                            // this job's x tile has been waited for
           mbar_wait(&t_full[ai], (job / R2P_ACCS) & 1);   // the accumulator's (job / 3)-th use (both groups use all three)
           tc_fence_after();
           if (trc) tp[1] = clock64();
@@ -270,8 +264,6 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
             uint32_t acc[16];
             __syncwarp();
             tmem_ld16(tacc + fb, acc);
-            uint4 xn[2];
-            if (has_next && k + 1 < n_blk) load_x(xn, fb + 16);
             tmem_ld_wait();
             uint32_t wv[8];                              // wv[q] = {frame fb + 2q, frame fb + 2q + 1} of channel ch
 #pragma unroll
@@ -317,24 +309,29 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
                   if (f >= T - 1 - H && f <= T - 2) *reinterpret_cast<uint4*>(vrow + static_cast<long>(2 * (T - 1) - f) * ld) = y;
                 }
                 if (has_next && !(SD_R2P_DBG & 4)) {
-                  // next conv's input x_{i+1} + y_i, from the f16-rounded y_i as an unfused chain would read it back
-                  // (one f16 add equals round_f16(float(x) + float(y)) bit for bit)
-                  uint4 sk;
-                  const __half2* ah = reinterpret_cast<const __half2*>(&xa[z]);
-                  const __half2* yh = reinterpret_cast<const __half2*>(&y);
-                  __half2* sh = reinterpret_cast<__half2*>(&sk);
+                  // next conv's input: y_i added onto the x tile the producer put into the slot's buffer, from the
+                  // f16-rounded y_i as an unfused chain would read it back (one f16 add equals
+                  // round_f16(float(x) + float(y)) bit for bit).  The mirrored halo rows hold u's own reflect halo,
+                  // bit-identical to the frames they mirror, so adding the same y gives the same sums.
+                  if (!x_seen) {
+                    mbar_wait(&x_full[s], (r * R2_CONVS + i + 1) & 1);
+                    x_seen = true;
+                  }
+                  auto add_y = [&](int p) {
+                    uint4* const q4 = reinterpret_cast<uint4*>(acol + p * 128 + ((piece ^ (p & 7)) << 4));
+                    uint4 sk = *q4;
+                    __half2* sh = reinterpret_cast<__half2*>(&sk);
+                    const __half2* yh = reinterpret_cast<const __half2*>(&y);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) sh[e] = __hadd2(ah[e], yh[e]);
-                  const int p = f + d;
-                  *reinterpret_cast<uint4*>(acol + p * 128 + ((piece ^ (p & 7)) << 4)) = sk;
-                  int p2 = -1;
-                  if (f >= 1 && f <= d) p2 = d - f;
-                  else if (f >= T - 1 - d && f <= T - 2) p2 = d + 2 * (T - 1) - f;
-                  if (p2 >= 0) *reinterpret_cast<uint4*>(acol + p2 * 128 + ((piece ^ (p2 & 7)) << 4)) = sk;
+                    for (int e = 0; e < 4; ++e) sh[e] = __hadd2(sh[e], yh[e]);
+                    *q4 = sk;
+                  };
+                  add_y(f + d);
+                  if (f >= 1 && f <= d) add_y(d - f);
+                  else if (f >= T - 1 - d && f <= T - 2) add_y(d + 2 * (T - 1) - f);
                 }
               }
             }
-            if (has_next && k + 1 < n_blk) { xa[0] = xn[0]; xa[1] = xn[1]; }
           }
           if (trc) tp[2] = clock64();
           // the accumulator is drained and the next input complete: hand both to the MMA warp
@@ -346,13 +343,6 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
             if (has_next) mbar_arrive(&a_ready[s]);
           }
           if (trc) tp[3] = clock64();
-          // pull the x sub-band the window's NEXT convolution will add (sub-band i + 3) from HBM into L2 now, four
-          // jobs ahead of its use: the loads above then pay an L2 hit instead of a DRAM round trip
-          if (SD_R2P_L2PF && i + 3 < 8) {
-            const __half* const xp = P.u + (i + 3) * R2_SUB + (wrow + H) * ld;
-            for (int idx = gw * 32 + lane; idx < 2 * T; idx += 256)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + static_cast<size_t>(idx >> 1) * ld + (idx & 1) * 64));
-          }
         }
     }
     if (kTrackOflow && amax > kHalfMax && P.oflow != nullptr) atomicOr(P.oflow, 1);
