@@ -343,6 +343,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
       Res2Params& Q = pr.r2[b];
       memset(&Q, 0, sizeof(Q));
       SD_TRY(make_tmap_f16(&Q.tmapU, p->u, R, C1, C1, T + 2 * bw.dil));
+      SD_TRY(make_tmap_f16_interior_plain(&Q.tmapV, p->v, C1, pr.Tp, T, HALO, B, 32, 16));
       for (int i = 0; i < 7; ++i) {
         SD_TRY(make_tmap_f16(&Q.tmapW[i], bw.res[i].W, SUB, 3 * SUB, 3 * SUB, SUB));
         SD_TRY(make_tmap_f16(&Q.tmapWh[i], bw.res[i].W, SUB, 3 * SUB, 3 * SUB, SUB / 2));
@@ -527,6 +528,7 @@ int build_front(SdEcapaPlan* p, Program& pr) {
     Q.u = pr.r2[0].u + row0 * C1;
     Q.v = pr.r2[0].v + row0 * C1;
     SD_TRY(make_tmap_f16(&Q.tmapU, Q.u, nrows, C1, C1, pr.T + 2 * Q.dil));
+    SD_TRY(make_tmap_f16_interior_plain(&Q.tmapV, Q.v, C1, pr.Tp, pr.T, HALO, nb, 32, 16));
   }
   return SD_OK;
 }

@@ -67,6 +67,26 @@ inline int make_tmap_f16_interior(CUtensorMap* m, const void* base, long ld, int
   return r == CUDA_SUCCESS ? SD_OK : SD_ERR_DRIVER;
 }
 
+// The same 3-D view {channels, T interior frames, windows} with a small UNSWIZZLED box (box_cols channels x box_rows
+// frames x 1 window; box_cols * 2 bytes a multiple of 16): the target of per-warp TMA stores from a row-major staging
+// tile (res2net_pipe.cuh).  Frames >= T are clipped on store, so a partial last block cannot touch the padding rows.
+inline int make_tmap_f16_interior_plain(CUtensorMap* m, const void* base, long ld, int Tp, int T, int H, int B,
+                                        int box_cols, int box_rows) {
+  PFN_tmapEncodeTiled enc = get_tmap_encoder();
+  if (!enc) return SD_ERR_DRIVER;
+  const char* p = static_cast<const char*>(base) + static_cast<size_t>(H) * ld * 2;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld * 2) % 16 || (box_cols * 2) % 16 || box_rows < 1 || box_rows > 256)
+    return SD_ERR_ARG;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(Tp) * ld * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<char*>(p), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SD_OK : SD_ERR_DRIVER;
+}
+
 // cudaFuncSetAttribute is per device: remember which devices already have it for a given kernel
 inline bool attr_needed(bool (&done)[64]) {
   int dev = 0;

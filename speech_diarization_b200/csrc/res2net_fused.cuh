@@ -52,6 +52,7 @@ struct alignas(64) Res2Params {
   CUtensorMap tmapU;              // u [rows, ld] f16, box = 64 channels x (T + 2*dil) rows
   CUtensorMap tmapW[R2_CONVS];    // conv i weights [128 out, 3 taps * 128 in] f16, box = 64 x 128
   CUtensorMap tmapWh[R2_CONVS];   // the same tensor, box = 64 x 64: half a weight box (2-CTA multicast, res2net_pipe.cuh)
+  CUtensorMap tmapV;              // v as {channels, T frames, windows}, unswizzled box 32 x 16 x 1 (res2net_pipe.cuh's y stores)
   const float* bias[R2_CONVS];
   const float* scale[R2_CONVS];
   const float* shift[R2_CONVS];

@@ -61,8 +61,9 @@ constexpr int R2P_THREADS = 64 + R2P_GROUPS * 256;   // warp 0 TMA, warp 1 MMA, 
 constexpr int R2P_RA = 160;                       // rows of an input buffer: T + 2 * dil <= 160
 constexpr int R2P_A_CHUNK = R2P_RA * 128;         // bytes per 64-channel chunk (20 x 1024)
 constexpr int R2P_A_BYTES = 2 * R2P_A_CHUNK;
-constexpr int R2P_WSLOTS = 4;
-constexpr int R2P_SMEM = R2P_SLOTS * R2P_A_BYTES + R2P_WSLOTS * R2_WBOX + 256;
+constexpr int R2P_WSLOTS = 3;
+constexpr int R2P_YSTAGE = 16 * 1024;             // per epilogue warp: [16 frames][32 channels] f16, the source of a TMA store
+constexpr int R2P_SMEM = R2P_SLOTS * R2P_A_BYTES + R2P_WSLOTS * R2_WBOX + R2P_YSTAGE + 256;
 static_assert(R2P_A_CHUNK % 1024 == 0, "input chunks must keep the swizzle alignment");
 static_assert(R2P_SMEM <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 
@@ -77,9 +78,10 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
   pdl_trigger();
   uint8_t* const abuf = smem;                                        // [slot][chunk][R2P_RA rows][128 B]
   uint8_t* const wring = smem + R2P_SLOTS * R2P_A_BYTES;
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(wring + R2P_WSLOTS * R2_WBOX);
-  uint64_t* const w_full = bars;            // [4] weight box landed
-  uint64_t* const w_empty = bars + 4;       // [4] its MMAs retired
+  uint8_t* const ystage = wring + R2P_WSLOTS * R2_WBOX;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(ystage + R2P_YSTAGE);
+  uint64_t* const w_full = bars;            // [3] weight box landed        (room for 4)
+  uint64_t* const w_empty = bars + 4;       // [3] its MMAs retired
   uint64_t* const x_full = bars + 8;        // [4] a slot's x tile landed (TMA): x_1 of a new window, or x_{i+2} after conv i
   uint64_t* const a_ready = bars + 12;      // [4] the epilogue added y_i onto it: the next convolution's input is complete (8 arrivals)
   uint64_t* const b_done = bars + 16;       // [4] a convolution's MMAs have finished reading the slot's buffer
@@ -235,6 +237,9 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
     const int tcol = quarter * 32 + 8 * tg;
     const int piece = (quarter & 1) * 4 + tg;     // 16-byte piece of the 128-byte input-buffer row
     const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4;
+    uint8_t* const my_stage = ystage + (warp - 2) * 1024;
+    bool store_pending = false;                   // lane 0: a TMA store of this warp may still be reading my_stage
+    if (lane == 0) tma_prefetch_desc(&P.tmapV);
     const int f_lo = 80 * half;
     const int n_blk = f_lo < T ? (min(T, f_lo + 80) - f_lo + 15) >> 4 : 0;   // 16-frame blocks this warp works through
     float amax = 0.f;
@@ -265,6 +270,9 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
             __syncwarp();
             tmem_ld16(tacc + fb, acc);
             tmem_ld_wait();
+            // the staging tile of the previous block's TMA store must have been read before it is rewritten
+            if (lane == 0 && store_pending) tma_store_wait_read();
+            __syncwarp();
             uint32_t wv[8];                              // wv[q] = {frame fb + 2q, frame fb + 2q + 1} of channel ch
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -301,10 +309,12 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
               const uint32_t r0 = __shfl_xor_sync(0xffffffffu, g0, 4), r1 = __shfl_xor_sync(0xffffffffu, g1, 4);
               const uint4 y = b2 ? make_uint4(r0, r1, k0, k1) : make_uint4(k0, k1, r0, r1);   // lanes c, c^4 -> eight channels
               const int f = fb + tr + 8 * z;
+              // y_i -> the warp's staging tile [16 frames][64 B]; it leaves as ONE TMA store per block below (per-lane
+              // 16-byte global stores cost ~6 k of the epilogue's ~9 k cycles).  Only the few mirrored halo rows the
+              // next layer's taps read are stored from the registers.
+              *reinterpret_cast<uint4*>(my_stage + (tr + 8 * z) * 64 + tg * 16) = y;
               if (f < T) {
-                // y_i -> v (+ the mirrored halo rows the next layer's taps read)
                 if (!(SD_R2P_DBG & 1)) {
-                  *reinterpret_cast<uint4*>(vrow + static_cast<long>(f) * ld) = y;
                   if (f >= 1 && f <= H) *reinterpret_cast<uint4*>(vrow - static_cast<long>(f) * ld) = y;
                   if (f >= T - 1 - H && f <= T - 2) *reinterpret_cast<uint4*>(vrow + static_cast<long>(2 * (T - 1) - f) * ld) = y;
                 }
@@ -332,6 +342,14 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
                 }
               }
             }
+            // the block's 16 frames x 32 channels of y_i: staging tile -> v (frames >= T are clipped by the tensor map)
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && !(SD_R2P_DBG & 1)) {
+              tma_store_3d(&P.tmapV, my_stage, (i + 1) * R2_SUB + quarter * 32, fb, w);
+              tma_store_commit();
+              store_pending = true;
+            }
           }
           if (trc) tp[2] = clock64();
           // the accumulator is drained and the next input complete: hand both to the MMA warp
@@ -345,6 +363,7 @@ res2net_pipe_kernel(const __grid_constant__ Res2Params P) {
           if (trc) tp[3] = clock64();
         }
     }
+    if (lane == 0 && store_pending) tma_store_wait_all();   // the staging tile must outlive the last store's read
     if (kTrackOflow && amax > kHalfMax && P.oflow != nullptr) atomicOr(P.oflow, 1);
   }
 
