@@ -274,6 +274,26 @@ def torch_gpu_bench(state_dict, audio_dev: torch.Tensor, frames_host: np.ndarray
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
 
+    # the same model under torch.autocast(float16): the library path at THIS repo's activation precision
+    def step_f16(i):
+        b = i % n_batches
+        with torch.inference_mode(), torch.autocast("cuda", dtype=torch.float16):
+            e = eo.encode_batch(model, frames_dev[b * BATCH:(b + 1) * BATCH]).squeeze(1)
+            return torch.nn.functional.normalize(e.float(), dim=1)
+    ms_f16 = None
+    try:
+        for i in range(warmup):
+            step_f16(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            step_f16(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_f16 = e0.elapsed_time(e1) / steps
+    except Exception as ex:                                   # a baseline leg must not take the bench down
+        print(f"[bench] torch f16 autocast leg failed: {ex}", file=sys.stderr)
+
     def e2e_step(i):
         b = i % n_batches
         with torch.inference_mode():
@@ -297,7 +317,10 @@ def torch_gpu_bench(state_dict, audio_dev: torch.Tensor, frames_host: np.ndarray
                            "pageable memory -> .to(device) -> encode_batch -> .cpu().numpy()"},
             "kind": "stock PyTorch " + torch.__version__ + " eager (cuDNN/cuBLAS/cuFFT), allow_tf32=True as "
                     "diarization_baseline.py:20-21, f32 activations; model = oracle/ecapa_oracle.ECAPA_TDNN on the GPU",
-            "dtype": "tf32"}
+            "dtype": "tf32",
+            "f16_autocast": None if ms_f16 is None else
+            {"value": BATCH / (ms_f16 * 1e-3), "ms_per_step": ms_f16,
+             "kind": "same model and steps under torch.autocast('cuda', float16)"}}
 
 
 def run_torch_gpu_arm(args, rank: int, local_rank: int) -> None:
@@ -319,7 +342,7 @@ def run_torch_gpu_arm(args, rank: int, local_rank: int) -> None:
           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
           "scaling": "weak", "vs_baseline": None, "dtype": r["dtype"], "data": "synthetic",
           "config": {"workload": WORKLOAD, "window_s": 1.5, "hop_s": 0.75, "batch": BATCH, "library": r["kind"]},
-          "clocks": clk, "e2e": r["e2e"], "gpu_launches": 0})
+          "clocks": clk, "e2e": r["e2e"], "f16_autocast": r["f16_autocast"], "gpu_launches": 0})
 
 
 # ---------------------------------------------------------------------------------- AHC leg
@@ -836,6 +859,9 @@ def main() -> None:
             try:
                 line["library_baseline"] = torch_gpu_bench(sd, audio, frames_pageable, device, min(args.steps, 10), 3)
                 line["library_baseline"]["speedup_value"] = value / line["library_baseline"]["value"]
+                if line["library_baseline"].get("f16_autocast"):
+                    line["library_baseline"]["speedup_value_vs_f16_autocast"] = (
+                        value / line["library_baseline"]["f16_autocast"]["value"])
                 line["library_baseline"]["speedup_e2e_vs_reference_call"] = (
                     e2e_legs["pageable_batch"]["value"] / line["library_baseline"]["e2e"]["value"])
             except Exception as e:
