@@ -70,6 +70,10 @@ int sd_fbank_num_frames(int n_samples);
 #define SD_FBANK_SPEECHBRAIN 1
 int sd_fbank_f32(const float* wav_dev, long wav_stride, int B, int n_samples, int variant,
                  int mean_norm, float* out_dev, void* stream);
+/* Measurement switch: which = 1 selects the tensor-core DFT frames kernel (default; $SD_FBANK_TC=0 starts with the
+ * other), which = 0 the FFT kernel on the FP32 pipe, which < 0 only queries.  Returns the kernel now selected.  Both
+ * implement the same operator; a change applies to later calls (a captured ECAPA plan graph keeps what it recorded). */
+int sd_fbank_kernel(int which);
 
 /* ------------------------------------------------------------- ECAPA-TDNN ---
  * A plan owns the f16-repacked weights (speechbrain ECAPA_TDNN, C = 1024,

@@ -27,6 +27,7 @@ SIGNATURES = {
     "sd_launch_count": (c_long, []),
     "sd_fbank_num_frames": (c_int, [c_int]),
     "sd_fbank_f32": (c_int, [c_void_p, c_long, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sd_fbank_kernel": (c_int, [c_int]),
     "sd_ecapa_plan_create": (c_int, [POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_int, c_int, POINTER(c_void_p)]),
     "sd_ecapa_plan_destroy": (c_int, [c_void_p]),
     "sd_ecapa_embed": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -102,7 +102,7 @@ struct SdEcapaPlan {
   // activations
   __half *feats = nullptr, *x0 = nullptr, *cat = nullptr, *u = nullptr, *v = nullptr, *w = nullptr;
   __half *s[2] = {nullptr, nullptr}, *h = nullptr, *attn = nullptr;
-  float *raw = nullptr, *se_mean = nullptr, *se_hid = nullptr, *se_scale = nullptr, *stats = nullptr;
+  float *raw = nullptr, *raw2 = nullptr, *se_mean = nullptr, *se_hid = nullptr, *se_scale = nullptr, *stats = nullptr;
   float *cs_se = nullptr, *cs_mfa = nullptr, *cq_mfa = nullptr;  // per (m block, window slot) column sums from the GEMM write-outs
   float *uttbias = nullptr, *pooled = nullptr, *emb_tmp = nullptr, *ctx_part = nullptr;
   int* oflow = nullptr;       // [0] an activation of the current forward left the f16 range (reset per forward),
@@ -947,6 +947,7 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
     SD_TRY(dev_alloc(p, (void**)&p->h, R * C3 * 2, true));
     SD_TRY(dev_alloc(p, (void**)&p->attn, R * ATT * 2, true));
     SD_TRY(dev_alloc(p, (void**)&p->raw, R * 80 * 4, true));
+    SD_TRY(dev_alloc(p, (void**)&p->raw2, R * 80 * 4, true));
     const size_t MB = (size_t)p->max_rows / tp_of(2 * HALO + 2) + 1;  // most utterances any shape can have
     SD_TRY(dev_alloc(p, (void**)&p->se_mean, MB * C1 * 4, true));
     SD_TRY(dev_alloc(p, (void**)&p->se_scale, MB * C1 * 4, true));
@@ -1013,7 +1014,7 @@ extern "C" int sd_ecapa_embed(SdEcapaPlan* p, const float* wav_dev, long wav_str
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mark(p, st);  // start of fbank
   SD_TRY(fbank_launch(wav_dev, wav_stride, B, n_samples, SD_FBANK_SPEECHBRAIN, 1, p->raw, nullptr,
-                      p->feats, pr->Tp, HALO, st));
+                      p->feats, pr->Tp, HALO, st, nullptr, p->raw2));
   return run_trunk(p, *pr, l2_normalize, emb_dev, st);
 }
 
@@ -1028,7 +1029,7 @@ extern "C" int sd_ecapa_embed_offsets(SdEcapaPlan* p, const float* wav_dev, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mark(p, st);  // start of fbank
   SD_TRY(fbank_launch(wav_dev, 0, B, n_samples, SD_FBANK_SPEECHBRAIN, 1, p->raw, nullptr, p->feats, pr->Tp, HALO, st,
-                      offsets_dev));
+                      offsets_dev, p->raw2));
   return run_trunk(p, *pr, l2_normalize, emb_dev, st);
 }
 
@@ -1102,7 +1103,8 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
     SD_CUDA_OK(cudaStreamWaitEvent(st, p->copy_ev[c], 0));
     SD_TRY(fbank_launch(p->h2d_buf + static_cast<size_t>(b0) * wav_stride, wav_stride, b1 - b0, n_samples,
                         SD_FBANK_SPEECHBRAIN, 1, p->raw + static_cast<size_t>(b0) * T * 80, nullptr,
-                        p->feats + static_cast<size_t>(b0) * pr->Tp * FEAT_P, pr->Tp, HALO, st));
+                        p->feats + static_cast<size_t>(b0) * pr->Tp * FEAT_P, pr->Tp, HALO, st, nullptr,
+                        p->raw2 + static_cast<size_t>(b0) * T * 80));
     if (piped) SD_TRY(front_body(p, *pr, c, st));
     return SD_OK;
   };
