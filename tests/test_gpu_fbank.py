@@ -18,6 +18,17 @@ pytestmark = pytest.mark.gpu
 TOL_LOG, TOL_DB = 1e-3, 3e-3
 
 
+@pytest.fixture(params=[0, 1], ids=["fft", "tensorcore"], autouse=True)
+def fbank_kernel(request):
+    """Every test of this file runs on both frames kernels: the FFT on the FP32 pipe (default) and the folded
+    split-f16 DFT on the tensor cores (sd_fbank_kernel(1))."""
+    lib = _lib.load()
+    before = lib.sd_fbank_kernel(-1)
+    lib.sd_fbank_kernel(request.param)
+    yield request.param
+    lib.sd_fbank_kernel(before)
+
+
 @pytest.mark.parametrize("tag", ["short", "win15"])
 def test_fbank_batch_matches_reference_golden(tag):
     g = golden(f"fbank_ref_{tag}.npz")
@@ -75,3 +86,46 @@ def test_fbank_error_behaviour():
     with pytest.raises(_lib.SdError):
         se.fbank_batch(np.zeros((2, 100), np.float32))        # shorter than one frame
     assert se.fbank_batch(np.zeros((0, 4000), np.float32)).shape == (0, 26, 80)
+
+
+@pytest.mark.parametrize("scale", [1e-5, 1e-3, 30.0, 3e4])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fbank_input_scale_invariance(variant, scale):
+    """Quiet and loud inputs (the tensor-core kernel rescales every span by a power of two, so neither the f16 lo part
+    nor the f16 range is a limit): log-mel of s*x == log-mel of x + log(s^2) wherever no floor is active."""
+    if variant == 0 and scale < 1e-2:
+        pytest.skip("log(x + 1e-6): a 1e-6 floor leaves nothing to compare at this scale")
+    w = synth_wave(2, 8000, 21)
+    a = se.fbank_batch_device(torch.from_numpy(w).cuda(), variant=variant, mean_nor=False).double().cpu().numpy()
+    b = se.fbank_batch_device(torch.from_numpy(w * np.float32(scale)).cuda(), variant=variant, mean_nor=False).double().cpu().numpy()
+    assert np.isfinite(b).all()
+    if variant == 1:
+        shift = 20.0 * np.log10(scale)
+        ok = (a > a.max() - 70.0) & (b > b.max() - 70.0) & (a > -90.0) & (b > -90.0)   # away from the top_db / amin floors
+        assert ok.sum() >= 100
+        assert np.abs((b - a - shift)[ok]).max() < TOL_DB
+    else:
+        pa, pb = np.exp(a) - 1e-6, np.exp(b) - 1e-6                                   # undo log(x + 1e-6)
+        ok = (pa > 1e-1) & (pb > 1e-1)
+        assert ok.sum() >= 100
+        assert np.abs(np.log(pb[ok] / pa[ok]) - 2 * np.log(scale)).max() < TOL_LOG
+
+
+def test_fbank_kernels_agree_on_embeddings(oracle_model):
+    """The two frames kernels feed the same ECAPA trunk: embeddings agree to 1 - cos < 1e-6."""
+    lib = _lib.load()
+    before = lib.sd_fbank_kernel(-1)
+    y = torch.from_numpy(synth_wave(1, 16000 * 8, 33)[0]).cuda()
+    out = []
+    try:
+        for which in (0, 1):
+            lib.sd_fbank_kernel(which)
+            enc = se.EcapaEncoderB200(oracle_model.state_dict(), device="cuda:0", max_batch=16, max_samples=24000)
+            try:
+                out.append(enc.embed_device(y, 12000, 9, 24000).double())
+            finally:
+                enc.close()
+    finally:
+        lib.sd_fbank_kernel(before)
+    cos = torch.nn.functional.cosine_similarity(out[0], out[1], dim=1)
+    assert float((1 - cos).max()) < 1e-5
