@@ -125,6 +125,7 @@ struct SdEcapaPlan {
   bool use_r2pipe = true;  // SD_R2_PIPE=0: res2net_fused_kernel (one window per CTA) instead of res2net_pipe_kernel
   bool use_pdl = false;    // SD_ECAPA_PDL=1: programmatic dependent launch between the trunk's kernels (measured
                            // 2 % SLOWER inside the replayed graph: 3.70-3.74 vs 3.64-3.66 ms per step)
+  bool use_tma_out_reflect = true;  // SD_ECAPA_TMAOUT0=0: block0 writes its tile with thread stores like the other layers
   bool use_tma_out = false; // SD_ECAPA_TMAOUT=1: the cta_group::2 GEMMs of the pointwise layers hand their staged tile to TMA
                             // tensor stores.  Measured 3 % SLOWER than the per-thread write-out (tdnn1 0.144 -> 0.148 ms): the
                             // launch is bound by operand ingest next to the store traffic, not by the epilogue threads' time
@@ -267,8 +268,23 @@ int setup_tdnn_gemm(GemmParams& P, const __half* A, long rows, int a_cols, int l
 // Pointwise layer on the cta_group::2 kernel: hand the staged tile to TMA tensor stores (EF_TMA_OUT).  The maps
 // cover exactly the columns this layer owns, so clipping at the tensor bounds replaces the row / column guards.
 int enable_tma_out(SdEcapaPlan* p, GemmParams& P) {
-  if (!p->use_2sm || !p->use_tma_out || (P.epi.flags & EF_REFLECT) || P.n_tile != 256) return SD_OK;
+  if (!p->use_2sm || P.n_tile != 256) return SD_OK;
   EpiParams& E = P.epi;
+  if (E.flags & EF_REFLECT) {
+    // block0 (k = 5): the one 256-wide layer whose EPILOGUE sets the pace (10 k-iterations per tile), so freeing
+    // its threads from the 64 KB write-out pays.  The halo rows are mirrored inside the staging tile, which needs
+    // every window's halo rows and their mirror sources in the same 128-row tile.
+    if (!p->use_tma_out_reflect || E.out2 != nullptr || E.sum_out != nullptr || E.colsum != nullptr) return SD_OK;
+    const int H = E.H, T = E.T, Tp = E.Tp;
+    if (Tp % EPI_WARPS != 0) return SD_OK;
+    for (long b = 0; b < 128 && b * Tp < E.M_rows; ++b) {   // the (window start mod 128) pattern repeats within 128 windows
+      const long s0 = b * Tp;
+      if (s0 / BM != (s0 + 2 * H) / BM) return SD_OK;                       // rows t = -H .. H
+      if ((s0 + H + T - 1 - H) / BM != (s0 + H + T - 1 + H) / BM) return SD_OK;   // rows t = T-1-H .. T-1+H
+    }
+  } else if (!p->use_tma_out) {
+    return SD_OK;
+  }
   SD_TRY(make_tmap_f16(&P.tmapH, static_cast<__half*>(E.out) + E.out_col_off, E.M_rows, E.N_cols, E.ld_out, BM));
   if (E.out2 != nullptr) SD_TRY(make_tmap_f16(&P.tmapO2, E.out2, E.M_rows, E.out2_cols, E.ld_out2, BM));
   E.flags |= EF_TMA_OUT;
@@ -302,6 +318,7 @@ int build_program(SdEcapaPlan* p, int B, int T, Program** out) {
   // block0: k = 5 over the 128-padded mel channels
   SD_TRY(setup_tdnn_gemm(pr.block0, p->feats, R, FEAT_P, FEAT_P, p->w0, C1, 5 * FEAT_P, 256, FEAT_P,
                          5, 1, 0, pr, p->x0, C1, 0, EF_REFLECT, p->use_mc || p->use_2sm));
+  SD_TRY(enable_tma_out(p, pr.block0));
   for (int b = 0; b < 3; ++b) {
     const __half* in = b == 0 ? p->x0 : p->cat + (size_t)(b - 1) * C1;
     const int ld_in = b == 0 ? C1 : C3;
@@ -854,7 +871,8 @@ extern "C" int sd_ecapa_plan_create(const char* const* names, const float* const
   if (const char* e = getenv("SD_ECAPA_R2FUSED")) p->use_r2fused = atoi(e) != 0;
   if (const char* e = getenv("SD_R2_PIPE")) p->use_r2pipe = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_COLSUM")) p->use_colsum = atoi(e) != 0;
-  if (const char* e = getenv("SD_ECAPA_TMAOUT")) p->use_tma_out = SD_EXPERIMENTS && atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_TMAOUT")) p->use_tma_out = atoi(e) != 0;
+  if (const char* e = getenv("SD_ECAPA_TMAOUT0")) p->use_tma_out_reflect = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_KSPLIT")) p->ksplit = atoi(e) < 1 ? 1 : atoi(e) > KSPLIT_MAX ? KSPLIT_MAX : atoi(e);
   if (const char* e = getenv("SD_ECAPA_L2ORDER")) p->use_l2_order = atoi(e) != 0;
   if (const char* e = getenv("SD_ECAPA_MC")) p->use_mc = SD_EXPERIMENTS && atoi(e) != 0;

@@ -44,6 +44,9 @@ constexpr int GEMM_THREADS = 320;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
+#ifndef SD_CPRE
+#define SD_CPRE 1   // 0: A/B build that fetches the epilogue constants at the top of each tile (round-1 behaviour)
+#endif
 // Epilogue warps per CTA, per epilogue kind.  The attentive-pooling epilogue (EPI_POOL) does ~14 instructions of
 // softmax / moment arithmetic per frame-channel; POOL_EPI_WARPS = 16 (four warps per TMEM lane quarter, 576
 // threads) was built and measured: the launch got SLOWER (0.27-0.29 -> 0.355 ms), so 8 stays.
@@ -1292,25 +1295,38 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;
-    const bool tma_out = SD_EXPERIMENTS && (P.epi.flags & EF_TMA_OUT) != 0;
+    const bool tma_out = (P.epi.flags & EF_TMA_OUT) != 0;
     if (tma_out && et == 0) {
       tma_prefetch_desc(&P.tmapH);
       if (P.epi.out2 != nullptr) tma_prefetch_desc(&P.tmapO2);
     }
     int last_n_blk = -1, as = 0;
     uint32_t aphase = 0;
+    float cpre[3] = {0.f, 1.f, 0.f};   // next tile's {bias, scale, shift} of column `et`, requested a tile ahead
+    int cpre_blk = -1;
     for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int m_unit = tile / P.num_n_blocks;
       const int n_blk = tile - m_unit * P.num_n_blocks;
       const int m_blk = 2 * m_unit + crank;
       if (n_blk != last_n_blk) {
+        // this n block's per-column constants -> shared.  With 74 CTA pairs on 4 (or 12) n blocks the block changes
+        // on every tile, so the three values were requested during the previous tile's write-out (cpre below):
+        // fetched here they cost an L2 round trip per tile on the epilogue's critical path (block0: 2.1 k of 9 k cycles).
         last_n_blk = n_blk;
-        for (int i = et; i < P.n_tile; i += EPI_THREADS) {
-          const int col = n_blk * P.n_tile + i;
-          const bool ok = col < P.epi.N_cols;
-          epi_sp[i] = (ok && P.epi.bias) ? P.epi.bias[col] : 0.f;
-          epi_sp[256 + i] = (ok && P.epi.scale) ? P.epi.scale[col] : 1.f;
-          epi_sp[512 + i] = (ok && P.epi.shift) ? P.epi.shift[col] : 0.f;
+        if (cpre_blk == n_blk) {
+          if (et < P.n_tile) {
+            epi_sp[et] = cpre[0];
+            epi_sp[256 + et] = cpre[1];
+            epi_sp[512 + et] = cpre[2];
+          }
+        } else {
+          for (int i = et; i < P.n_tile; i += EPI_THREADS) {
+            const int col = n_blk * P.n_tile + i;
+            const bool ok = col < P.epi.N_cols;
+            epi_sp[i] = (ok && P.epi.bias) ? P.epi.bias[col] : 0.f;
+            epi_sp[256 + i] = (ok && P.epi.scale) ? P.epi.scale[col] : 1.f;
+            epi_sp[512 + i] = (ok && P.epi.shift) ? P.epi.shift[col] : 0.f;
+          }
         }
         epi_named_barrier();
       }
@@ -1336,6 +1352,48 @@ gemm_tc_2sm_kernel(const __grid_constant__ GemmParams P) {
       if (++as == 2) { as = 0; aphase ^= 1; }
       epi_named_barrier();  // staging tile complete
       if (tr) tp[4] = clock64();
+      {
+        // request the next tile's constants now: the loads complete under this tile's write-out
+        const int nt = tile + tstep;
+        cpre_blk = -1;
+        if (SD_CPRE && nt < num_tiles && P.n_tile <= EPI_THREADS) {
+          const int nb = nt - (nt / P.num_n_blocks) * P.num_n_blocks;
+          if (nb != n_blk) {
+            cpre_blk = nb;
+            const int col = nb * P.n_tile + et;
+            const bool ok = et < P.n_tile && col < P.epi.N_cols;
+            cpre[0] = (ok && P.epi.bias) ? P.epi.bias[col] : 0.f;
+            cpre[1] = (ok && P.epi.scale) ? P.epi.scale[col] : 1.f;
+            cpre[2] = (ok && P.epi.shift) ? P.epi.shift[col] : 0.f;
+          }
+        }
+      }
+      if (tma_out && (P.epi.flags & EF_REFLECT)) {
+        // k > 1 layer leaving through TMA: the tile's halo rows were computed from rows outside the window, so they
+        // are replaced IN THE STAGING TILE by their mirror images (interior row t = j for halo row t = -j, row
+        // T-1-j for T-1+j; the host enables this path only when a window's halo and its sources share a tile) and
+        // the pad rows behind the halo by zeros — what the thread write-out does with r2 / r3 and `valid`.
+        const EpiParams& E = P.epi;
+        const int we = et >> 5, ln = et & 31;
+        const int cj = ln >> 3, sub = ln & 7;
+        uint8_t* sc = stage_out + cj * 16384;
+        int pw = (m_blk * BM + we) % E.Tp;
+        for (int rl = we; rl < BM; rl += EPI_WARPS) {
+          const int t = pw - E.H;
+          int src = -2;                               // -2 keep, -1 zero, >= 0 copy that staging row
+          if (t < 0) src = rl - 2 * t;
+          else if (t >= E.T) src = (t - (E.T - 1) <= E.H) ? rl - 2 * (t - (E.T - 1)) : -1;
+          if (src != -2) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (src >= 0 && src < BM) v = *reinterpret_cast<const uint4*>(sc + src * 128 + ((sub ^ (src & 7)) << 4));
+            *reinterpret_cast<uint4*>(sc + rl * 128 + ((sub ^ (rl & 7)) << 4)) = v;
+          }
+          pw += EPI_WARPS;
+          if (pw >= E.Tp) pw -= E.Tp;
+        }
+        fence_proxy_async();
+        epi_named_barrier();
+      }
       if (tma_out) {
         if (et == 0) {
           // four [128 rows x 64 channels] boxes, already in the 128-byte-swizzled layout; rows >= M_rows are clipped
