@@ -20,6 +20,7 @@
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
+#include <chrono>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -1057,6 +1058,11 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
   if (n_samples < 400 || wav_stride < 1)
     return fail(SD_ERR_ARG, "sd_ecapa_embed_host: n_samples=%d stride=%ld", n_samples, wav_stride);
   const int T = 1 + n_samples / 160;
+  // SD_HOST_TRACE=1: host-side timeline of each call on stderr (us since entry): queued-uploads, queued-trunk, synced, exit
+  static const bool host_trace = getenv("SD_HOST_TRACE") != nullptr;
+  const auto ht0 = std::chrono::steady_clock::now();
+  auto ht_us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - ht0).count(); };
+  double ht[4] = {0, 0, 0, 0};
   SD_TRY(check_shape(p, B, T));
   Program* pr = nullptr;
   SD_TRY(build_program(p, B, T, &pr));
@@ -1184,7 +1190,9 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
       SD_TRY(launch_chunk(c));
     }
   }
+  ht[0] = ht_us();
   SD_TRY(run_trunk(p, *pr, l2_normalize, p->emb_stage, st, piped));
+  ht[1] = ht_us();
   const size_t emb_bytes = static_cast<size_t>(B) * EMB * sizeof(float);
   SD_CUDA_OK(cudaMemcpyAsync(p->emb_pinned ? p->emb_pinned : emb_host, p->emb_stage, emb_bytes, cudaMemcpyDeviceToHost, st));
   if (!p->oflow_host && cudaHostAlloc(reinterpret_cast<void**>(&p->oflow_host), sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
@@ -1193,7 +1201,12 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
   }
   if (p->oflow_host) SD_CUDA_OK(cudaMemcpyAsync(p->oflow_host, p->oflow + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   SD_CUDA_OK(cudaStreamSynchronize(st));
+  ht[2] = ht_us();
   if (p->emb_pinned) memcpy(emb_host, p->emb_pinned, emb_bytes);
+  ht[3] = ht_us();
+  if (host_trace)
+    fprintf(stderr, "[sd host trace] B=%d uploads+fbank queued %.0f us, trunk queued %.0f, synced %.0f, copied out %.0f\n", B,
+            ht[0], ht[1], ht[2], ht[3]);
   if (p->oflow_host && *p->oflow_host != 0) {
     cudaMemsetAsync(p->oflow + 1, 0, sizeof(int), st);
     return fail(SD_ERR_RANGE, "sd_ecapa_embed_host: an activation left the f16 range (|x| > 65504) and was saturated; "
