@@ -18,7 +18,7 @@
 //      whose cached nearest neighbour was merged (reducibility keeps every other cache valid).
 // It stops when no RNN pair is below the threshold, which — average linkage being monotone —
 // is the flat clustering sklearn cuts at `distance_threshold`.  The whole loop is ONE
-// persistent cooperative kernel (grid-wide barriers between phases — four per round: A | B | C1+C2 | C3+D — and no
+// persistent cooperative kernel (grid-wide barriers between phases — three per round: A | B | C+D — and no
 // host round trips).
 // Arithmetic is f64 on the f32-rounded input, as in scipy.  The matrix is HBM-resident
 // (8 N^2 bytes: 3.2 GB at N = 20k, 20 GB at 50k).
@@ -48,6 +48,8 @@ struct AhcState {
   int* dirty_list;  // [N]
   int* pair_i;      // [N/2]
   int* pair_j;      // [N/2]
+  int* pair_ni;     // [N/2] sizes of the two clusters when the pair was found (phase C reads these, phase D updates `size`)
+  int* pair_nj;     // [N/2]
   int* act_list;    // [2][N] compact list of live clusters (ping-pong)
   int* counters;    // [0],[1] n_dirty ping-pong [2] n_pairs [3] rounds [4] merges [5] list length [6] list index
                     // [7] live clusters [8] staged new list length
@@ -110,27 +112,6 @@ __global__ void ahc_init_state_kernel(AhcState S) {
   }
 }
 
-// Grid-wide barrier of the (cooperatively launched, hence co-resident) grid: one arrival per CTA on a monotonic
-// counter, thread 0 spins with acquire loads.  Four of these per round, ~300-600 rounds per call: cheaper than
-// cooperative_groups' grid.sync() by ~1.5 us each (SD_AHC_CGSYNC=1 at compile time restores it).
-#ifndef SD_AHC_CGSYNC
-#define SD_AHC_CGSYNC 0
-#endif
-__device__ __forceinline__ void ahc_grid_barrier(unsigned int* counter, unsigned int& epoch) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    epoch += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    unsigned int seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-    } while (seen < epoch);
-    __threadfence();
-  }
-  __syncthreads();
-}
-
 __device__ __forceinline__ void argmin_combine(double& d, int& i, double od, int oi) {
   if (od < d || (od == d && oi < i)) { d = od; i = oi; }
 }
@@ -151,12 +132,8 @@ ahc_rounds_kernel(AhcState S) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gtid = blockIdx.x * AHC_THREADS + tid;
   const int gthreads = gridDim.x * AHC_THREADS;
-  unsigned int bar_epoch = 0;
-  unsigned int* const bar_counter = reinterpret_cast<unsigned int*>(S.counters + 12);
-  auto grid_sync = [&]() {
-    if (SD_AHC_CGSYNC) grid.sync();
-    else ahc_grid_barrier(bar_counter, bar_epoch);
-  };
+  // (a hand-rolled one-arrival-per-CTA barrier instead of grid.sync() was measured: 24.0 vs 24.05 ms at N = 20k)
+  auto grid_sync = [&]() { grid.sync(); };
   int cur = 0;  // which dirty counter is current
   long long t_prev = S.prof ? ahc_now() : 0;
   auto stamp = [&](int phase) {
@@ -235,6 +212,8 @@ ahc_rounds_kernel(AhcState S) {
         const int p = atomicAdd(&S.counters[2], 1);
         S.pair_i[p] = r;
         S.pair_j[p] = j;
+        S.pair_ni[p] = S.size[r];
+        S.pair_nj[p] = S.size[j];
         S.role[r] = 2 * p;
         S.role[j] = 2 * p + 1;
       }
@@ -244,47 +223,22 @@ ahc_rounds_kernel(AhcState S) {
     const int n_pairs = S.counters[2];
     if (n_pairs == 0) break;
 
-    // ---- C1: rows.  D[i,k] <- (n_i D[i,k] + n_j D[j,k]) / (n_i + n_j) for every live k
+    // ---- C: the Lance-Williams update of every pair, rows, corners and mirrored column by the SAME CTA, no grid
+    // barrier in between (it used to be rows + upper corners | barrier | mirror).  Who writes what:
+    //   row i_p, columns k that do not merge this round ........ CTA p (C1), then mirrored into D[k, i_p] (C3)
+    //   corner (i_p, i_q), i_p < i_q .............................. CTA p: C1 on columns i_q and j_q, C2 combines them,
+    //                                                              and CTA p also writes the mirror image D[i_q, i_p]
+    //   row i_p, columns i_q < i_p ................................ never touched by CTA p (CTA q writes them)
+    // so no entry has two writers, and every value a CTA combines comes from rows i_p / j_p, which only CTA p writes.
+    // The cluster sizes are the snapshot phase B took (pair_ni / pair_nj): phase D below updates `size` concurrently.
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const int i = S.pair_i[p], j = S.pair_j[p];
-      const double ni = S.size[i], nj = S.size[j], inv = ni + nj;
+      const double ni = S.pair_ni[p], nj = S.pair_nj[p], inv = ni + nj;
       MT* ri = DM + static_cast<size_t>(i) * N;
       const MT* rj = DM + static_cast<size_t>(j) * N;
       for (int q0 = tid; q0 < n_list; q0 += AHC_THREADS * AHC_U) {
-        int k[AHC_U];
-        double a[AHC_U], b[AHC_U];
-#pragma unroll
-        for (int u = 0; u < AHC_U; ++u) {
-          const int q = q0 + u * AHC_THREADS;
-          k[u] = q < n_list ? list[q] : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < AHC_U; ++u)
-          if (k[u] >= 0) { a[u] = ri[k[u]]; b[u] = rj[k[u]]; }
-#pragma unroll
-        for (int u = 0; u < AHC_U; ++u)
-          if (k[u] >= 0) ri[k[u]] = static_cast<MT>((ni * a[u] + nj * b[u]) / inv);
-      }
-      // ---- C2: corners between two merged clusters (upper triangle only, i_p < i_q).  They combine two entries of
-      // THIS row, both just written by this CTA, so a CTA barrier is enough (this used to be a phase of its own)
-      __syncthreads();
-      for (int q = tid; q < n_pairs; q += AHC_THREADS) {
-        const int iq = S.pair_i[q], jq = S.pair_j[q];
-        if (i < iq) {
-          const double nq = S.size[iq], mq = S.size[jq];
-          ri[iq] = static_cast<MT>((nq * static_cast<double>(ri[iq]) + mq * static_cast<double>(ri[jq])) / (nq + mq));
-        }
-      }
-    }
-    grid_sync();
-    stamp(2);
-    // ---- C3: mirror row i_p into column i_p (and the lower corners from the upper ones)
-    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-      const int i = S.pair_i[p];
-      MT* ri = DM + static_cast<size_t>(i) * N;
-      for (int q0 = tid; q0 < n_list; q0 += AHC_THREADS * AHC_U) {
         int k[AHC_U], rk[AHC_U], act[AHC_U];
-        MT v[AHC_U];
+        double a[AHC_U], b[AHC_U];
 #pragma unroll
         for (int u = 0; u < AHC_U; ++u) {
           const int q = q0 + u * AHC_THREADS;
@@ -293,17 +247,36 @@ ahc_rounds_kernel(AhcState S) {
 #pragma unroll
         for (int u = 0; u < AHC_U; ++u) {
           act[u] = 0;
-          if (k[u] >= 0 && k[u] != i) { act[u] = S.active[k[u]]; rk[u] = S.role[k[u]]; v[u] = ri[k[u]]; }
+          rk[u] = -1;
+          a[u] = b[u] = 0.0;
+          if (k[u] >= 0 && k[u] != i) { act[u] = S.active[k[u]]; rk[u] = S.role[k[u]]; a[u] = ri[k[u]]; b[u] = rj[k[u]]; }
         }
 #pragma unroll
         for (int u = 0; u < AHC_U; ++u) {
-          if (!act[u]) continue;
-          if (rk[u] >= 0 && (rk[u] & 1)) continue;  // absorbed this round
-          if (rk[u] >= 0 && k[u] < i) ri[k[u]] = DM[static_cast<size_t>(k[u]) * N + i];
-          else DM[static_cast<size_t>(k[u]) * N + i] = v[u];
+          // live columns; a column that merges this round counts as live whatever `active` says (phase D of another
+          // CTA may already have retired an absorbed cluster whose entry C2 below still needs)
+          if (!(act[u] || rk[u] >= 0) || k[u] < 0 || k[u] == i) continue;
+          if (rk[u] >= 0 && !(rk[u] & 1) && k[u] < i) continue;   // corner owned by the CTA of row k
+          const MT v = static_cast<MT>((ni * a[u] + nj * b[u]) / inv);
+          ri[k[u]] = v;
+          if (rk[u] < 0) DM[static_cast<size_t>(k[u]) * N + i] = v;   // C3: column i of a row that does not merge
         }
       }
+      __syncthreads();
+      // C2: corners with the pairs of larger row index, combined from this row's two freshly updated entries,
+      // written to both triangles
+      for (int q = tid; q < n_pairs; q += AHC_THREADS) {
+        const int iq = S.pair_i[q], jq = S.pair_j[q];
+        if (i < iq) {
+          const double nq = S.pair_ni[q], mq = S.pair_nj[q];
+          const MT v = static_cast<MT>((nq * static_cast<double>(ri[iq]) + mq * static_cast<double>(ri[jq])) / (nq + mq));
+          ri[iq] = v;
+          DM[static_cast<size_t>(iq) * N + i] = v;
+        }
+      }
+      __syncthreads();
     }
+    stamp(2);
     // ---- D (same phase: touches size/parent/dirty only): retire absorbed clusters, mark dirty rows
     const int nxt = cur ^ 1;
     for (int q = gtid; q < n_list; q += gthreads) {
@@ -455,6 +428,8 @@ extern "C" int sd_ahc_average_f32(const float* dist_dev, int N, double threshold
   S.pair_i = ip + 6 * static_cast<size_t>(N);
   S.pair_j = S.pair_i + (N + 1) / 2;  // at most floor(N/2) pairs per round
   int* scratch = ip + 7 * static_cast<size_t>(N);
+  S.pair_ni = scratch;                 // the label kernel's scratch is free while the rounds run
+  S.pair_nj = scratch + (N + 1) / 2;
   S.counters = ip + 8 * static_cast<size_t>(N);
   S.act_list = ip + 8 * static_cast<size_t>(N) + 64;
   S.prof = getenv("SD_AHC_PROF") ? reinterpret_cast<long long*>(S.counters + 16) : nullptr;
