@@ -1191,7 +1191,13 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
     }
   }
   ht[0] = ht_us();
+  static cudaEvent_t ht_ev[2] = {nullptr, nullptr};
+  if (host_trace) {
+    if (!ht_ev[0]) { cudaEventCreate(&ht_ev[0]); cudaEventCreate(&ht_ev[1]); }
+    cudaEventRecord(ht_ev[0], st);
+  }
   SD_TRY(run_trunk(p, *pr, l2_normalize, p->emb_stage, st, piped));
+  if (host_trace) cudaEventRecord(ht_ev[1], st);
   ht[1] = ht_us();
   const size_t emb_bytes = static_cast<size_t>(B) * EMB * sizeof(float);
   SD_CUDA_OK(cudaMemcpyAsync(p->emb_pinned ? p->emb_pinned : emb_host, p->emb_stage, emb_bytes, cudaMemcpyDeviceToHost, st));
@@ -1204,9 +1210,12 @@ extern "C" int sd_ecapa_embed_host(SdEcapaPlan* p, const float* wav_host, long w
   ht[2] = ht_us();
   if (p->emb_pinned) memcpy(emb_host, p->emb_pinned, emb_bytes);
   ht[3] = ht_us();
-  if (host_trace)
-    fprintf(stderr, "[sd host trace] B=%d uploads+fbank queued %.0f us, trunk queued %.0f, synced %.0f, copied out %.0f\n", B,
-            ht[0], ht[1], ht[2], ht[3]);
+  if (host_trace) {
+    float trunk_ms = 0.f;
+    cudaEventElapsedTime(&trunk_ms, ht_ev[0], ht_ev[1]);
+    fprintf(stderr, "[sd host trace] B=%d uploads+fbank queued %.0f us, trunk queued %.0f, synced %.0f, copied out %.0f; "
+            "trunk on the device %.0f us (from the last fbank to the embeddings)\n", B, ht[0], ht[1], ht[2], ht[3], 1e3f * trunk_ms);
+  }
   if (p->oflow_host && *p->oflow_host != 0) {
     cudaMemsetAsync(p->oflow + 1, 0, sizeof(int), st);
     return fail(SD_ERR_RANGE, "sd_ecapa_embed_host: an activation left the f16 range (|x| > 65504) and was saturated; "

@@ -9,6 +9,10 @@
 // when that chunk's samples have landed.  Page-locked callers' buffers bypass all this (direct DMA).
 #pragma once
 #include <cuda_runtime.h>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
+#include <stdlib.h>
 #include <atomic>
 #include <condition_variable>
 #include <cstring>
@@ -106,6 +110,38 @@ class StagingRing {
     size_t len;
     std::atomic<int>* done;
   };
+  // Copy into the pinned ring with NON-TEMPORAL stores: a plain memcpy leaves the 2 MB piece dirty in the copying
+  // core's cache, and the DMA engine then reads it through cache snoops at ~15 GB/s (measured: the H2D copies of a
+  // 24.6 MB batch took 1.4 ms from the ring against 0.43 ms from cold page-locked memory); streamed past the cache
+  // it is read from DRAM at the PCIe rate.  dst is 64-byte aligned (ring slots), src is not.
+  static void stream_copy(char* dst, const char* src, size_t len) {
+#if defined(__x86_64__) || defined(_M_X64)
+    if (!stream_stores()) {
+      std::memcpy(dst, src, len);
+      return;
+    }
+    size_t i = 0;
+    for (; i + 64 <= len; i += 64) {
+      const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+      const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+      const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+    }
+    if (i < len) std::memcpy(dst + i, src + i, len - i);
+    _mm_sfence();
+#else
+    std::memcpy(dst, src, len);
+#endif
+  }
+  static bool stream_stores() {   // SD_ECAPA_STAGING_NT=0: plain memcpy (A/B)
+    static const bool on = [] { const char* e = getenv("SD_ECAPA_STAGING_NT"); return !e || atoi(e) != 0; }();
+    return on;
+  }
+
   void work() {
     for (;;) {
       Job j;
@@ -116,7 +152,7 @@ class StagingRing {
         j = jobs_.front();
         jobs_.erase(jobs_.begin());
       }
-      std::memcpy(j.dst, j.src, j.len);
+      stream_copy(j.dst, j.src, j.len);
       j.done->store(1, std::memory_order_release);
     }
   }

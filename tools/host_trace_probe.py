@@ -9,7 +9,7 @@ speech_encode.register_ecapa_state_dict(random_ecapa_state_dict(0))
 rng = np.random.default_rng(0)
 y = (0.1 * rng.standard_normal(16000 * 1200)).astype(np.float32)
 pin = torch.from_numpy(y).pin_memory()
-fr = vad.frame_audio(pin.numpy(), 16000, 1500.0, 750.0)
+fr = vad.frame_audio(y if "--pageable" in sys.argv else pin.numpy(), 16000, 1500.0, 750.0)
 for i in range(3): speech_encode.ecapa_encode_batch(fr[i * 512:(i + 1) * 512])
 torch.cuda.synchronize()
 t_prev = time.perf_counter()
