@@ -160,6 +160,11 @@ ahc_rounds_kernel(AhcState S) {
       S.role[S.pair_i[p]] = -1;
       S.role[S.pair_j[p]] = -1;
     }
+    // the pair counter of the previous round: every thread read it right after that round's B barrier, and a whole
+    // barrier (the one that ended the round) lies between that read and this reset; B of this round, which counts
+    // again, is behind the barrier that ends this phase.  (Resetting it at the end of the round, as before phase C3
+    // lost its barrier, let a slow CTA read 0 and leave the loop: wrong partitions at N = 50k.)
+    if (gtid == 0) S.counters[2] = 0;
     for (int q = blockIdx.x; q < n_dirty; q += gridDim.x) {
       const int r = S.dirty_list[q];
       const MT* row = DM + static_cast<size_t>(r) * N;
@@ -326,8 +331,7 @@ ahc_rounds_kernel(AhcState S) {
       }
       if (tid == AHC_THREADS - 1) S.counters[8] = scan_s[tid];  // new length, picked up by every thread at the top of the next round
     }
-    if (gtid == 0) {   // n_pairs was read by everyone two barriers ago; statistics for sd_ahc_read_stats
-      S.counters[2] = 0;
+    if (gtid == 0) {   // statistics for sd_ahc_read_stats (the pair counter itself is reset in the next round's phase A)
       S.counters[3] = round + 1;
       S.counters[4] += n_pairs;
       S.counters[7] = n_alive_after;

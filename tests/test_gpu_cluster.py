@@ -117,6 +117,30 @@ def test_ahc_properties_at_n20k():
     assert co.same_partition(got_p, got[perm])
 
 
+def test_ahc_repeated_runs_agree():
+    """The round loop is a chain of grid-wide phases over shared counters: repeated runs must give the same labels, the
+    same number of rounds and N - K merges (a counter reset one barrier too early once let a slow CTA leave the loop:
+    right answer on most runs, wrong partition on some)."""
+    for n, k in ((6000, 8), (20000, 8)):
+        X, lab = synth_emb(n, k, 0.02, 11)
+        dist = cl.cosine_distance_device(torch.from_numpy(X).cuda())
+        cl.ahc_keep_stats(True)
+        try:
+            first, stats0 = None, None
+            for rep in range(6):
+                got, ncl = cl.ahc_average_device(dist, 1 - 0.68)
+                stats = cl.ahc_last_stats()
+                g = got.cpu().numpy()
+                assert int(ncl.item()) == k and stats["merges"] == n - k
+                if first is None:
+                    first, stats0 = g, stats
+                    assert co.same_partition(g, lab)
+                else:
+                    assert np.array_equal(g, first) and stats == stats0
+        finally:
+            cl.ahc_keep_stats(False)
+
+
 @pytest.mark.parametrize("tag", ["clean", "edge"])
 def test_ahc_n20k_labels_match_reference_golden(tag):
     """BASELINE config 4 at N = 20 000 against the labels of the reference's own cluster_embeddings (diar_diag.py:213-229;
