@@ -575,7 +575,8 @@ __device__ __forceinline__ void pool_chunks_regs(const GemmParams& P, uint32_t t
   }
   const float mx = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
   const float mxs = (mx == -INFINITY) ? 0.f : mx * LOG2E;
-  float se[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  float2 se2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, s12[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)},
+         s22[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c0 = (NP * i + half) * 16;
@@ -592,20 +593,26 @@ __device__ __forceinline__ void pool_chunks_regs(const GemmParams& P, uint32_t t
         for (int j = 0; j < 16; ++j)
           if (t0 + j < 0 || t0 + j >= E.T) xv[j] = 0.f;  // weight is exactly 0; keep 0 * garbage out
       }
+      // two frames per instruction (sm_100's packed f32x2 FMA / ADD / MUL): the same IEEE operations in the same
+      // order as the scalar loop — accumulator j & 3 is lane j & 1 of pair (j >> 1) & 1 — at half the issue slots
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float e = ex2_approx(fmaf(__uint_as_float(v[i][j]), LOG2E, -mxs));
-        se[j & 3] += e;
-        const float ex = e * xv[j];
-        s1[j & 3] += ex;
-        s2[j & 3] = fmaf(ex, xv[j], s2[j & 3]);
+      for (int j = 0; j < 16; j += 2) {
+        const float2 arg = fma2(make_float2(__uint_as_float(v[i][j]), __uint_as_float(v[i][j + 1])),
+                                make_float2(LOG2E, LOG2E), make_float2(-mxs, -mxs));
+        const float2 e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+        const float2 x2 = make_float2(xv[j], xv[j + 1]);
+        const int a = (j >> 1) & 1;
+        se2[a] = add2(se2[a], e);
+        const float2 ex = mul2(e, x2);
+        s12[a] = add2(s12[a], ex);
+        s22[a] = fma2(ex, x2, s22[a]);
       }
     }
   }
   st.mx = mx;
-  st.se = (se[0] + se[1]) + (se[2] + se[3]);
-  st.s1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
-  st.s2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+  st.se = (se2[0].x + se2[0].y) + (se2[1].x + se2[1].y);
+  st.s1 = (s12[0].x + s12[0].y) + (s12[1].x + s12[1].y);
+  st.s2 = (s22[0].x + s22[0].y) + (s22[1].x + s22[1].y);
 }
 
 __device__ __forceinline__ void epilogue_pool(const GemmParams& P, int m_blk, int n_blk, int sub,

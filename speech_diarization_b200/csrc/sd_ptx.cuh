@@ -302,6 +302,31 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int n, int ab_format
   return d;
 }
 
+// ------------------------------------------------------------ packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2)
+// Two independent round-to-nearest f32 operations per instruction: the results equal the scalar ones bit for bit.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(r)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(r)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(r)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+
 // ------------------------------------------------------------ small helpers
 // Two f32 -> one packed f16x2 (a in the low half), round-to-nearest, SATURATING: a finite value beyond the f16
 // range becomes +-65504 instead of +-inf, so one out-of-range activation (a real checkpoint with a large
