@@ -138,3 +138,26 @@ def test_host_buffer_path_equals_device_path(oracle_model, monkeypatch):
         np.testing.assert_array_equal(host["view"][:70], host["dense"])
     finally:
         speech_encode.register_ecapa_state_dict(None)
+
+
+def test_sharded_embedding_from_host_slice_equals_device_path(oracle_model):
+    """embed_windows_sharded_host (chunked upload on a side stream, overlapped with the embedding of the previous
+    chunk) returns exactly what embed_windows_sharded returns for the same samples already on the device."""
+    from conftest import synth_wave
+    y = synth_wave(1, 16000 * 60, 12)[0]
+    enc = se.EcapaEncoderB200(oracle_model.state_dict(), device="cuda:0", max_batch=64, max_samples=24000)
+    try:
+        ref, rng_ref = sharded.embed_windows_sharded(torch.from_numpy(y).cuda(), 24000, 12000, enc)
+        for pinned in (True, False):
+            host = torch.from_numpy(y.copy())
+            if pinned:
+                host = host.pin_memory()
+            t = {}
+            got, rng = sharded.embed_windows_sharded_host(host, 24000, 12000, enc, n_total_samples=y.size, timings=t,
+                                                           chunk_windows=17)
+            assert rng == rng_ref and torch.equal(got, ref)
+            assert "upload_and_embed_shard" in t
+        with pytest.raises(ValueError):
+            sharded.embed_windows_sharded_host(torch.from_numpy(y[:1000].copy()), 24000, 12000, enc, n_total_samples=y.size)
+    finally:
+        enc.close()
